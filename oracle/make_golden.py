@@ -1,0 +1,220 @@
+"""Oracle (test infrastructure): generate tests/golden/*.npz by RUNNING THE REFERENCE ITSELF.
+
+Run in the authoring container only (needs /root/reference, read-only):
+
+    python -m oracle.make_golden
+
+Imports the unmodified reference modules (pyrender / matplotlib / ultralytics are absent and
+unused by the hot path, so empty stubs are put in sys.modules first -- SURVEY.md F8) and
+records their outputs on seeded synthetic scenes:
+
+  geometry.npz   per scene: inputs, compute_fundamental_matrix x3, compute_cost_matrix (the
+                 as-written triple loop), match_objects + the sort of process_pose.py:183,
+                 PoseEstimator._match (called unbound) -> boxes / centroids / t, and
+                 compute_reprojection_error per view.
+  bop_scene.npz  config 1: a temp BOP directory read back through Capture.from_dir so the
+                 f32 -> f64 dtype flow is the real one, then _match.
+  crops.npz      one source image, ROIs in all three INTER_AREA regimes, the reference's
+                 letterbox_preserving_aspect_ratio outputs (uint8), the normalisation table from
+                 torchvision's to_tensor/normalize, and full f32 tensors for a few crops.
+
+/root/reference does not exist on the GPU box: nothing else may import it.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import json
+import os
+import sys
+import tempfile
+import types
+from types import SimpleNamespace
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+REFERENCE = '/root/reference'
+
+
+def import_reference():
+    for name in ('pyrender', 'matplotlib', 'matplotlib.pyplot', 'ultralytics'):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules['matplotlib'].pyplot = sys.modules['matplotlib.pyplot']
+    sys.modules['ultralytics'].YOLO = object
+    if REFERENCE not in sys.path:
+        sys.path.insert(0, REFERENCE)
+    import bpc.inference.epipolar_matching as em
+    import bpc.inference.process_pose as pp
+    import bpc.inference.utils.camera_utils as cu
+    import bpc.inference.utils.triangulation as tri
+    import bpc.utils.data_utils as du
+    return SimpleNamespace(em=em, pp=pp, cu=cu, tri=tri, du=du)
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def run_match(ref, Ks, RTs, dets, threshold=30):
+    """Everything the reference computes for one scene, from its own functions."""
+    K1, K2, K3 = Ks
+    R = [x[:3, :3] for x in RTs]
+    t = [x[:3, 3] for x in RTs]
+    F12 = ref.cu.compute_fundamental_matrix(K1, R[0], t[0], K2, R[1], t[1])
+    F13 = ref.cu.compute_fundamental_matrix(K1, R[0], t[0], K3, R[2], t[2])
+    F23 = ref.cu.compute_fundamental_matrix(K2, R[1], t[1], K3, R[2], t[2])
+    out = {'F': np.stack([F12, F13, F23])}
+    params = ref.pp.PoseEstimatorParams(matching_threshold=threshold)
+    capture = SimpleNamespace(images=[None] * 3, Ks=Ks, RTs=RTs)
+    preds = quiet(ref.pp.PoseEstimator._match, SimpleNamespace(params=params), capture, dets)
+    n = len(preds)
+    out['boxes'] = np.array([p.boxes for p in preds], np.int64).reshape(n, 3, 4)
+    out['centroids'] = np.array([p.centroids for p in preds], np.float64).reshape(n, 3, 2)
+    out['X'] = np.array([p.t for p in preds], np.float64).reshape(n, 3)
+    if min(len(dets[0]), len(dets[1]), len(dets[2])) == 0:
+        out['cost'] = np.zeros((len(dets[0]), len(dets[1]), len(dets[2])), np.float32)
+        out['idx'] = np.zeros((0, 3), np.int64)
+        out['reproj'] = np.zeros((0, 3))
+        return out
+    cost = ref.em.compute_cost_matrix(dets[0], dets[1], dets[2], F12, F13, F23)
+    matches = ref.em.match_objects(cost, threshold=threshold)
+    matches = sorted(matches, key=lambda m: cost[m[0], m[1], m[2]])
+    out['cost'] = cost
+    out['idx'] = np.array(matches, np.int64).reshape(len(matches), 3)
+    # _match and the standalone calls must agree (same code, same inputs)
+    assert len(matches) == n
+    for m, p in zip(matches, preds):
+        for v in range(3):
+            assert tuple(p.boxes[v]) == tuple(dets[v][m[v]]['bbox'])
+    Ps = [K @ RT[:3] for K, RT in zip(Ks, RTs)]
+    out['reproj'] = np.array([[ref.tri.compute_reprojection_error(Ps[v], p.t, p.centroids[v])
+                               for v in range(3)] for p in preds]).reshape(n, 3)
+    return out
+
+
+def golden_geometry(ref):
+    from bpc_baseline_b200 import synth
+    cases = [
+        # name, D, kwargs, scenes
+        ('clean10', 10, dict(), 4),
+        ('clean20', 20, dict(), 2),
+        ('drop12', 12, dict(p_drop=0.25, sigma=2.0), 6),
+        ('dup8', 8, dict(n_dup=2), 4),
+        ('false9', 9, dict(n_false=3, p_drop=0.15), 4),
+        ('tiny3', 3, dict(p_drop=0.3), 6),
+        ('dense40', 40, dict(p_drop=0.1, sigma=2.0), 1),
+    ]
+    blob = {}
+    names = []
+    for name, D, kw, S in cases:
+        batch = synth.make_scenes(S, D, seed=synth.SEED + 1, **kw)
+        for s in range(S):
+            tag = f'{name}_{s}'
+            Ks, RTs = batch.capture_arrays(s)
+            dets = batch.detections(s)
+            if name == 'tiny3' and s == 5:          # a view with zero detections
+                dets[1] = []
+                batch.counts[s, 1] = 0
+            res = run_match(ref, Ks, RTs, dets)
+            names.append(tag)
+            blob[f'{tag}/Ks'] = batch.Ks[s]
+            blob[f'{tag}/RTs'] = batch.RTs[s]
+            blob[f'{tag}/boxes'] = batch.boxes[s]
+            blob[f'{tag}/centers'] = batch.centers[s]
+            blob[f'{tag}/counts'] = batch.counts[s]
+            for k, v in res.items():
+                blob[f'{tag}/ref_{k}'] = v
+            print(f'  {tag}: counts={batch.counts[s].tolist()} matches={len(res["idx"])}')
+    blob['names'] = np.array(names)
+    np.savez_compressed(os.path.join(GOLDEN, 'geometry.npz'), **blob)
+
+
+def golden_bop_scene(ref):
+    """Config 1: single IPD-style scene, obj_id 8, 3 cameras x 10 detections, through Capture.from_dir."""
+    import cv2
+    from bpc_baseline_b200 import synth
+    batch = synth.make_scenes(1, 10, seed=synth.SEED + 2)
+    cam_ids = ['cam1', 'cam2', 'cam3']
+    with tempfile.TemporaryDirectory() as d:
+        for c, cid in enumerate(cam_ids):
+            cam = {'0': {'cam_K': [float(v) for v in batch.Ks[0, c].reshape(-1)],
+                         'cam_R_w2c': [float(v) for v in batch.RTs[0, c, :3, :3].reshape(-1)],
+                         'cam_t_w2c': [float(v) for v in batch.RTs[0, c, :3, 3]],
+                         'depth_scale': 1.0}}
+            with open(os.path.join(d, f'scene_camera_{cid}.json'), 'w') as f:
+                json.dump(cam, f)
+            os.makedirs(os.path.join(d, f'rgb_{cid}'))
+            cv2.imwrite(os.path.join(d, f'rgb_{cid}', '000000.png'), np.zeros((16, 16, 3), np.uint8))
+        cap = quiet(ref.du.Capture.from_dir, d, cam_ids, 0, 8)
+    assert all(k.dtype == np.float32 for k in cap.Ks) and all(rt.dtype == np.float64 for rt in cap.RTs)
+    res = run_match(ref, cap.Ks, cap.RTs, batch.detections(0))
+    blob = {'Ks': np.stack(cap.Ks), 'RTs': np.stack(cap.RTs), 'boxes': batch.boxes[0],
+            'centers': batch.centers[0], 'counts': batch.counts[0]}
+    blob.update({f'ref_{k}': v for k, v in res.items()})
+    print(f'  bop scene: matches={len(res["idx"])}')
+    np.savez_compressed(os.path.join(GOLDEN, 'bop_scene.npz'), **blob)
+
+
+def golden_crops(ref):
+    import cv2
+    import torch
+    import torchvision.transforms.functional as TF
+    from bpc_baseline_b200 import synth
+    H, W = 520, 648
+    image = synth.make_images(1, seed=synth.SEED + 3, width=W, height=H)[0]
+    rng = np.random.default_rng([synth.SEED, 3])
+    boxes = []
+    for _ in range(10):                                    # random sides, both regimes 1 and 3
+        w, h = rng.integers(24, 420, 2)
+        x1 = int(rng.integers(0, W - w + 1)); y1 = int(rng.integers(0, H - h + 1))
+        boxes.append((x1, y1, x1 + int(w), y1 + int(h)))
+    boxes += [(10, 20, 10 + 448, 20 + 448), (3, 5, 3 + 448, 5 + 224), (100, 7, 100 + 224, 7 + 224),
+              (5, 5, 5 + 512, 5 + 512), (7, 300, 7 + 512, 300 + 96), (640, 0, 648, 400), (0, 0, 9, 8),
+              (11, 13, 11 + 225, 13 + 223), (200, 100, 200 + 223, 100 + 224), (0, 0, 648, 520)]
+    blob = {'image': image, 'boxes': np.array(boxes, np.int32)}
+    for T in (224, 256, 64):
+        canv, geom = [], []
+        for (x1, y1, x2, y2) in (boxes if T != 256 else boxes[::2]):
+            crop = image[y1:y2, x1:x2]
+            letter, scale, dx, dy = ref.du.letterbox_preserving_aspect_ratio(
+                crop, target_size=T, fill_color=(255, 255, 255))
+            canv.append(letter)
+            geom.append((scale, dx, dy))
+        blob[f'canvas_T{T}'] = np.stack(canv)
+        blob[f'geom_T{T}'] = np.array(geom, np.float64)
+    # normalisation table from torchvision's own calls (process_pose.py:206-209)
+    ramp = np.arange(256, dtype=np.uint8).reshape(1, 256, 1).repeat(3, axis=2)       # "RGB" image
+    lut = TF.normalize(TF.to_tensor(ramp), [0.485, 0.456, 0.406], [0.229, 0.224, 0.225])
+    blob['lut'] = lut.numpy().reshape(3, 256)
+    # a few complete network inputs, the inline crop code of process_pose.py:199-209
+    tens = []
+    for (x1, y1, x2, y2) in boxes[:4]:
+        crop = image[y1:y2, x1:x2]
+        letter, _, _, _ = ref.du.letterbox_preserving_aspect_ratio(crop, target_size=64, fill_color=(255, 255, 255))
+        rgb = cv2.cvtColor(letter, cv2.COLOR_BGR2RGB)
+        t = TF.normalize(TF.to_tensor(rgb), [0.485, 0.456, 0.406], [0.229, 0.224, 0.225])
+        tens.append(t.numpy())
+    blob['tensor_T64'] = np.stack(tens)
+    blob['versions'] = np.array([f'cv2 {cv2.__version__}', f'torch {torch.__version__}', f'numpy {np.__version__}'])
+    np.savez_compressed(os.path.join(GOLDEN, 'crops.npz'), **blob)
+    print(f'  crops: {len(boxes)} boxes x T in (224, 64), every other box at T=256')
+
+
+def main():
+    if not os.path.isdir(REFERENCE):
+        raise SystemExit('needs /root/reference (authoring container only)')
+    sys.path.insert(0, ROOT)
+    os.makedirs(GOLDEN, exist_ok=True)
+    ref = import_reference()
+    print('geometry'); golden_geometry(ref)
+    print('bop scene'); golden_bop_scene(ref)
+    print('crops'); golden_crops(ref)
+
+
+if __name__ == '__main__':
+    main()
