@@ -1,0 +1,240 @@
+"""Batched, device-resident API over the C ABI (include/bpc_b200.h).
+
+torch is used for device memory and streams only; every computation is a kernel of
+libbpc_b200.so launched on torch's current stream.  All inputs must be contiguous CUDA tensors of
+the documented dtype; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MEAN = (0.485, 0.456, 0.406)   # process_pose.py:208
+STD = (0.229, 0.224, 0.225)    # process_pose.py:209
+
+
+def _chk(t: torch.Tensor, dtype, name: str, ndim: Optional[int] = None):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f'{name}: expected a torch.Tensor, got {type(t).__name__}')
+    if not t.is_cuda:
+        raise RuntimeError(f'{name}: must be a CUDA tensor (no CPU fallback)')
+    if t.dtype != dtype:
+        raise RuntimeError(f'{name}: dtype {t.dtype}, expected {dtype}')
+    if not t.is_contiguous():
+        raise RuntimeError(f'{name}: must be contiguous')
+    if ndim is not None and t.dim() != ndim:
+        raise RuntimeError(f'{name}: {t.dim()} dims, expected {ndim}')
+    return t
+
+
+def _p(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream(dev) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+@dataclass
+class MatchResult:
+    """Output of match_triangulate; rows of a scene are sorted by (cost, r) as process_pose.py:183."""
+    idx: torch.Tensor      # i32 [S, Kmax, 3]  (i, j, k), -1 padded
+    n: torch.Tensor        # i32 [S]           matches per scene (-1: infeasible costs, SciPy would raise)
+    cost: torch.Tensor     # f32 [S, Kmax]
+    X: torch.Tensor        # f64 [S, Kmax, 3]
+    reproj: Optional[torch.Tensor]   # f64 [S, Kmax, 3]
+    F: Optional[torch.Tensor]        # f64 [S, 3, 3, 3]
+
+
+def fundamental(Ks: torch.Tensor, RTs: torch.Tensor) -> torch.Tensor:
+    """F12, F13, F23 per scene: f64 [S,3,3,3] (camera_utils.py:23-46 via process_pose.py:154-159)."""
+    _chk(Ks, torch.float32, 'Ks', 4); _chk(RTs, torch.float64, 'RTs', 4)
+    S = Ks.shape[0]
+    if tuple(Ks.shape[1:]) != (3, 3, 3) or tuple(RTs.shape) != (S, 3, 4, 4):
+        raise RuntimeError('Ks must be [S,3,3,3] and RTs [S,3,4,4]')
+    F = torch.empty((S, 3, 3, 3), dtype=torch.float64, device=Ks.device)
+    with torch.cuda.device(Ks.device):
+        _lib.check(_lib.load().bpc_fundamental(_p(Ks), _p(RTs), S, _p(F), _stream(Ks.device)), 'bpc_fundamental')
+    return F
+
+
+def box_centers(boxes: torch.Tensor) -> torch.Tensor:
+    """centres f64 [..., 2] from int32 boxes [..., 4] (process_pose.py:134-136)."""
+    _chk(boxes, torch.int32, 'boxes')
+    if boxes.shape[-1] != 4:
+        raise RuntimeError('boxes must end in a dimension of 4')
+    out = torch.empty((*boxes.shape[:-1], 2), dtype=torch.float64, device=boxes.device)
+    with torch.cuda.device(boxes.device):
+        _lib.check(_lib.load().bpc_box_centers(_p(boxes), boxes.numel() // 4, _p(out), _stream(boxes.device)), 'bpc_box_centers')
+    return out
+
+
+def cost_tensor(F: torch.Tensor, centers: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    """Materialised cost f32 [S,Dmax,Dmax,Dmax] (epipolar_matching.py:83-98); entries beyond (N,M,P) are NaN."""
+    _chk(F, torch.float64, 'F', 4); _chk(centers, torch.float64, 'centers', 4); _chk(counts, torch.int32, 'counts', 2)
+    S, _, D, _ = centers.shape
+    if tuple(F.shape) != (S, 3, 3, 3) or tuple(centers.shape) != (S, 3, D, 2) or tuple(counts.shape) != (S, 3):
+        raise RuntimeError('shape mismatch between F, centers and counts')
+    cost = torch.full((S, D, D, D), float('nan'), dtype=torch.float32, device=F.device)
+    with torch.cuda.device(F.device):
+        _lib.check(_lib.load().bpc_cost_tensor(_p(F), _p(centers), _p(counts), S, D, _p(cost), _stream(F.device)), 'bpc_cost_tensor')
+    return cost
+
+
+def match_objects(cost: torch.Tensor, threshold) -> tuple[torch.Tensor, torch.Tensor]:
+    """LSAP + threshold on explicit cost f32 [S,N,M,P] -> (idx i32 [S,Kmax,3] ascending r, n i32 [S])."""
+    _chk(cost, torch.float32, 'cost', 4)
+    S, N, M, P = cost.shape
+    if N == 0 or M == 0 or P == 0:
+        raise RuntimeError('cost tensor has an empty dimension')
+    kmax = min(N * M, P)
+    idx = torch.empty((S, kmax, 3), dtype=torch.int32, device=cost.device)
+    n = torch.empty((S,), dtype=torch.int32, device=cost.device)
+    with torch.cuda.device(cost.device):
+        _lib.check(_lib.load().bpc_match_objects(_p(cost), S, N, M, P, float(np.float32(threshold)), _p(idx), _p(n),
+                                                 None, 0, _stream(cost.device)), 'bpc_match_objects')
+    return idx, n
+
+
+def match_triangulate(Ks: torch.Tensor, RTs: torch.Tensor, centers: torch.Tensor, counts: torch.Tensor,
+                      threshold=30, want_reproj: bool = True, want_F: bool = False) -> MatchResult:
+    """PoseEstimator._match (process_pose.py:144-188) for S scenes in one launch."""
+    _chk(Ks, torch.float32, 'Ks', 4); _chk(RTs, torch.float64, 'RTs', 4)
+    _chk(centers, torch.float64, 'centers', 4); _chk(counts, torch.int32, 'counts', 2)
+    S, _, D, _ = centers.shape
+    if tuple(Ks.shape) != (S, 3, 3, 3) or tuple(RTs.shape) != (S, 3, 4, 4) or tuple(centers.shape) != (S, 3, D, 2) \
+            or tuple(counts.shape) != (S, 3):
+        raise RuntimeError('expected Ks [S,3,3,3], RTs [S,3,4,4], centers [S,3,Dmax,2], counts [S,3]')
+    dev = Ks.device
+    idx = torch.empty((S, D, 3), dtype=torch.int32, device=dev)
+    n = torch.empty((S,), dtype=torch.int32, device=dev)
+    cost = torch.empty((S, D), dtype=torch.float32, device=dev)
+    X = torch.empty((S, D, 3), dtype=torch.float64, device=dev)
+    reproj = torch.empty((S, D, 3), dtype=torch.float64, device=dev) if want_reproj else None
+    F = torch.empty((S, 3, 3, 3), dtype=torch.float64, device=dev) if want_F else None
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().bpc_match_triangulate(
+            _p(Ks), _p(RTs), _p(centers), _p(counts), S, D, float(np.float32(threshold)),
+            _p(idx), _p(n), _p(cost), _p(X), _p(reproj), _p(F), None, 0, _stream(dev)), 'bpc_match_triangulate')
+    return MatchResult(idx, n, cost, X, reproj, F)
+
+
+def triangulate(P: torch.Tensor, pts: torch.Tensor) -> torch.Tensor:
+    """DLT for n matches: P f64 [n,3,3,4], pts f64 [n,3,2] -> X f64 [n,3] (epipolar_matching.py:118-127)."""
+    _chk(P, torch.float64, 'P', 4); _chk(pts, torch.float64, 'pts', 3)
+    n = P.shape[0]
+    if tuple(P.shape) != (n, 3, 3, 4) or tuple(pts.shape) != (n, 3, 2):
+        raise RuntimeError('expected P [n,3,3,4] and pts [n,3,2]')
+    X = torch.empty((n, 3), dtype=torch.float64, device=P.device)
+    with torch.cuda.device(P.device):
+        _lib.check(_lib.load().bpc_triangulate(_p(P), _p(pts), n, _p(X), _stream(P.device)), 'bpc_triangulate')
+    return X
+
+
+def reprojection_error(P: torch.Tensor, X: torch.Tensor, pts: torch.Tensor) -> torch.Tensor:
+    """Per-view pixel error f64 [n,3] (utils/triangulation.py:14-18)."""
+    _chk(P, torch.float64, 'P', 4); _chk(X, torch.float64, 'X', 2); _chk(pts, torch.float64, 'pts', 3)
+    n = P.shape[0]
+    err = torch.empty((n, 3), dtype=torch.float64, device=P.device)
+    with torch.cuda.device(P.device):
+        _lib.check(_lib.load().bpc_reprojection_error(_p(P), _p(X), _p(pts), n, _p(err), _stream(P.device)), 'bpc_reprojection_error')
+    return err
+
+
+def build_rois(boxes: torch.Tensor, idx: torch.Tensor, n: torch.Tensor, image_of_scene: torch.Tensor,
+               rois: Optional[torch.Tensor] = None) -> tuple[torch.Tensor, torch.Tensor]:
+    """(rois i32 [S*Kmax*3, 5], scene_offset i32 [S+1]); 3 ROIs per match in (scene, match, view) order.
+
+    scene_offset[S] (device) is the number of valid ROIs; rows beyond it are unspecified.
+    """
+    _chk(boxes, torch.int32, 'boxes', 4); _chk(idx, torch.int32, 'idx', 3); _chk(n, torch.int32, 'n', 1)
+    _chk(image_of_scene, torch.int32, 'image_of_scene', 2)
+    S, _, D, _ = boxes.shape
+    K = idx.shape[1]
+    dev = boxes.device
+    if rois is None:
+        rois = torch.empty((S * K * 3, 5), dtype=torch.int32, device=dev)
+    offs = torch.empty((S + 1,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().bpc_build_rois(_p(boxes), _p(idx), _p(n), _p(image_of_scene), S, D, K, _p(offs), _p(rois),
+                                              _stream(dev)), 'bpc_build_rois')
+    return rois, offs
+
+
+_LUT_CACHE: dict = {}
+
+
+def normalise_lut(device, mean: Sequence[float] = MEAN, std: Sequence[float] = STD) -> torch.Tensor:
+    """f32 [3,256] table: lut[c][v] = (v/255 - mean[c]) / std[c] in float32 (process_pose.py:207-209)."""
+    device = torch.device(device)
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tuple(mean), tuple(std))
+    if key not in _LUT_CACHE:
+        lut = torch.empty((3, 256), dtype=torch.float32, device=device)
+        m = (C.c_float * 3)(*[float(np.float32(v)) for v in mean])
+        s = (C.c_float * 3)(*[float(np.float32(v)) for v in std])
+        with torch.cuda.device(device):
+            _lib.check(_lib.load().bpc_normalise_lut(m, s, _p(lut), _stream(device)), 'bpc_normalise_lut')
+        _LUT_CACHE[key] = lut
+    return _LUT_CACHE[key]
+
+
+def _crop_args(images, rois, T, fill):
+    _chk(images, torch.uint8, 'images', 4); _chk(rois, torch.int32, 'rois', 2)
+    B, H, W, ch = images.shape
+    if ch != 3 or rois.shape[1] != 5:
+        raise RuntimeError('images must be [B,H,W,3] and rois [R,5]')
+    if not 1 <= int(T) <= 256:
+        raise RuntimeError('target size must be in 1..256')
+    f = (C.c_uint8 * 3)(*[int(v) for v in fill])
+    return B, H, W, rois.shape[0], f
+
+
+def roi_crop(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(255, 255, 255), swap_rb: bool = True,
+             lut: Optional[torch.Tensor] = None, n_rois: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Network inputs f32 [R,3,T,T] for R ROIs (data_utils.py:34-44 + process_pose.py:199-209).
+
+    ``n_rois``: optional device int32 scalar tensor; ROIs at or beyond it are skipped (their output
+    rows are left untouched).  ``status``: optional int32 [R], 1 where an ROI was rejected.
+    """
+    B, H, W, R, f = _crop_args(images, rois, T, fill)
+    dev = images.device
+    if lut is None:
+        lut = normalise_lut(dev)
+    _chk(lut, torch.float32, 'lut', 2)
+    if out is None:
+        out = torch.empty((R, 3, T, T), dtype=torch.float32, device=dev)
+    else:
+        _chk(out, torch.float32, 'out', 4)
+        if out.shape[0] < R or tuple(out.shape[1:]) != (3, T, T):
+            raise RuntimeError('out must be [>=R,3,T,T]')
+    if status is not None:
+        _chk(status, torch.int32, 'status', 1)
+    if n_rois is not None:
+        _chk(n_rois, torch.int32, 'n_rois')
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().bpc_roi_crop(_p(images), B, H, W, _p(rois), R, _p(n_rois), int(T), f, int(bool(swap_rb)),
+                                            _p(lut), _p(out), _p(status), _stream(dev)), 'bpc_roi_crop')
+    return out
+
+
+def roi_crop_u8(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(255, 255, 255),
+                n_rois: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Letterboxed uint8 crops [R,T,T,3] in source channel order (data_utils.py:34-44)."""
+    B, H, W, R, f = _crop_args(images, rois, T, fill)
+    dev = images.device
+    if out is None:
+        out = torch.empty((R, T, T, 3), dtype=torch.uint8, device=dev)
+    if status is not None:
+        _chk(status, torch.int32, 'status', 1)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().bpc_roi_crop_u8(_p(images), B, H, W, _p(rois), R, _p(n_rois), int(T), f, _p(out), _p(status),
+                                               _stream(dev)), 'bpc_roi_crop_u8')
+    return out

@@ -1,0 +1,55 @@
+"""Build libbpc_b200.so in-tree with nvcc for sm_100a (no GPU needed: nvcc cross-compiles).
+
+    python -m bpc_baseline_b200.build [--force] [--verbose]
+
+The shared library is a plain C-ABI object (include/bpc_b200.h); it does not link against torch.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, 'csrc')
+LIB = os.path.join(HERE, 'libbpc_b200.so')
+SOURCES = ['api.cu', 'match.cu', 'crop.cu']
+HEADERS = ['common.cuh', 'geometry.cuh', 'lsap.cuh']
+ARCH = ['-gencode', 'arch=compute_100a,code=sm_100a']
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get('NVCC'), shutil.which('nvcc'), '/usr/local/cuda/bin/nvcc'):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError('nvcc not found (set NVCC=/path/to/nvcc)')
+
+
+def stale() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(ROOT, 'include', 'bpc_b200.h')]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not stale():
+        return LIB
+    cmd = [nvcc_path(), '-shared', '-Xcompiler', '-fPIC', '-O3', '-std=c++17', '-lineinfo', '--fmad=false',
+           *ARCH, '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
+    if verbose:
+        cmd += ['-Xptxas', '-v']
+    cmd += [os.path.join(CSRC, f) for f in SOURCES] + ['-o', LIB]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed building libbpc_b200.so')
+    return LIB
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))

@@ -1,0 +1,595 @@
+// Geometry kernels of libbpc_b200: fundamental matrices, cost tensor, assignment, triangulation.
+//
+// bpc_match_triangulate = PoseEstimator._match (bpc/inference/process_pose.py:144-188) for a batch of
+// independent scenes, one CTA per scene, everything in shared memory / registers:
+//   phase 0  F12/F13/F23 (camera_utils.py:23-46), P = K @ RT[:3] (process_pose.py:91), two normalised
+//            epipolar lines per detection and camera pair (epipolar_matching.py:13-23);
+//   phase 1  one warp per third-camera detection k: exact argmin over the N*M (i, j) pairs of the VIRTUAL
+//            cost tensor (epipolar_matching.py:83-98 is never materialised), pruned with
+//            sum >= e13[i,k] and sum >= e23[j,k];
+//   phase 2  SciPy-exact assignment (lsap.cuh): rows whose argmin column is still free are immediate
+//            sinks; conflicts and exact ties run the full shortest-augmenting-path search;
+//   phase 3  threshold (epipolar_matching.py:110-111), sort by (cost, r) (process_pose.py:183), DLT
+//            triangulation and reprojection error per match, one thread each.
+#include "geometry.cuh"
+#include "lsap.cuh"
+
+namespace bpc {
+
+// ------------------------------------------------------------------------------------------------------
+// cost accessors for the assignment
+// ------------------------------------------------------------------------------------------------------
+struct VirtualCost {            // cost.reshape(N*M, P) of the epipolar cost tensor
+    const Scene* sc;
+    int transposed;             // 1: rows = k, cols = r = i*M + j   (N*M > P, SciPy transposes)
+    __device__ __forceinline__ double cost(int row, int col) const {
+        const int r = transposed ? col : row;
+        const int k = transposed ? row : col;
+        const int i = r / sc->M, j = r - i * sc->M;
+        return (double)sc->cost(i, j, k);
+    }
+};
+
+struct ExplicitCost {           // dense float32 [N*M][P]
+    const float* c;
+    int P;
+    int transposed;
+    __device__ __forceinline__ double cost(int row, int col) const {
+        const int r = transposed ? col : row;
+        const int k = transposed ? row : col;
+        return (double)c[(size_t)r * P + k];
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// phase 1: per-row argmin of the virtual cost tensor (transposed case), one warp per row k
+// ------------------------------------------------------------------------------------------------------
+struct RowMin {
+    float* cmin;   // [P] float32 cost of the best column
+    int* rlo;      // [P] lowest column index r attaining it
+    int* cnt;      // [P] number of columns attaining it (float32 equality)
+};
+
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = fmin(v, shfl_xor_d(v, m));
+    return v;
+}
+__device__ __forceinline__ int warp_min_i(int v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    return v;
+}
+
+// scratch per warp: a[Dmax], b[Dmax] doubles, il[Dmax], jl[Dmax] int16
+__device__ void row_argmin(const Scene& sc, int k, double* sa, double* sb, short* il, short* jl, RowMin out) {
+    const int lane = lane_id();
+    const int N = sc.N, M = sc.M;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    // a_i = e13[i,k], b_j = e23[j,k]
+    double amin = INF, bmin = INF;
+    int i0 = 0x7fffffff, j0 = 0x7fffffff;
+    for (int i = lane; i < N; i += 32) {
+        const double a = sc.e13(i, k);
+        sa[i] = a;
+        if (a < amin) { amin = a; i0 = i; }
+    }
+    for (int j = lane; j < M; j += 32) {
+        const double b = sc.e23(j, k);
+        sb[j] = b;
+        if (b < bmin) { bmin = b; j0 = j; }
+    }
+    const double wa = warp_min_d(amin), wb = warp_min_d(bmin);
+    i0 = warp_min_i(amin == wa ? i0 : 0x7fffffff);
+    j0 = warp_min_i(bmin == wb ? j0 : 0x7fffffff);
+    if (i0 >= N) i0 = 0;       // all-NaN guards
+    if (j0 >= M) j0 = 0;
+    __syncwarp();
+    // seed an upper bound from the row / column through the individually best i and j
+    double best = INF;
+    for (int j = lane; j < M; j += 32)
+        if (sb[j] <= best) best = fmin(best, dadd(dadd(sc.e12(i0, j), sa[i0]), sb[j]));
+    for (int i = lane; i < N; i += 32)
+        if (sa[i] <= best) best = fmin(best, dadd(dadd(sc.e12(i, j0), sa[i]), sb[j0]));
+    best = warp_min_d(best);
+    // every (i, j) whose float32 cost can equal the minimum has sum <= bound, hence a_i, b_j <= bound
+    // (sum = fl(fl(e12 + a) + b) >= max(a, b) because rounding is monotone and e12 >= 0)
+    const double bound = dadd(dmul(best, 1.0 + 2.384185791015625e-07), 1e-37);
+    int nI = 0, nJ = 0;
+    for (int base = 0; base < N; base += 32) {
+        const int i = base + lane;
+        const bool p = i < N && sa[i] <= bound;
+        const unsigned m = __ballot_sync(0xffffffffu, p);
+        if (p) il[nI + __popc(m & ((1u << lane) - 1))] = (short)i;
+        nI += __popc(m);
+    }
+    for (int base = 0; base < M; base += 32) {
+        const int j = base + lane;
+        const bool p = j < M && sb[j] <= bound;
+        const unsigned m = __ballot_sync(0xffffffffu, p);
+        if (p) jl[nJ + __popc(m & ((1u << lane) - 1))] = (short)j;
+        nJ += __popc(m);
+    }
+    __syncwarp();
+    const int npair = nI * nJ;
+    double smin = INF;
+    for (int q = lane; q < npair; q += 32) {
+        const int ii = q / nJ, jj = q - ii * nJ;
+        const int i = il[ii], j = jl[jj];
+        smin = fmin(smin, dadd(dadd(sc.e12(i, j), sa[i]), sb[j]));
+    }
+    smin = warp_min_d(smin);
+    const float cmin = cost_from_sum(smin);
+    int cnt = 0, rlo = 0x7fffffff;
+    for (int q = lane; q < npair; q += 32) {
+        const int ii = q / nJ, jj = q - ii * nJ;
+        const int i = il[ii], j = jl[jj];
+        const double s = dadd(dadd(sc.e12(i, j), sa[i]), sb[j]);
+        if (s <= bound && cost_from_sum(s) == cmin) { ++cnt; rlo = min(rlo, i * M + j); }
+    }
+    cnt = warp_sum_i(cnt);
+    rlo = warp_min_i(rlo);
+    if (lane == 0) { out.cmin[k] = cmin; out.cnt[k] = cnt; out.rlo[k] = rlo; }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// shared-memory layout of bpc_match_kernel
+// ------------------------------------------------------------------------------------------------------
+struct MatchSmem {
+    double* F;       // [3][9]
+    double* Pm;      // [3][12]
+    Scene sc;
+    LsapState st;
+    RowMin rm;
+    float* mcost;    // [Dmax] per assigned row
+    int* mr;         // [Dmax]
+    int* mk;         // [Dmax]
+    double* wa;      // [nwarps][Dmax]
+    double* wb;      // [nwarps][Dmax]
+    short* wil;      // [nwarps][Dmax]
+    short* wjl;      // [nwarps][Dmax]
+};
+
+static size_t match_smem_bytes(int Dmax, int nwarps) {
+    size_t b = 0;
+    b += (27 + 36) * 8;
+    b += (size_t)3 * Dmax * 2 * 8;                  // pts
+    b += (size_t)6 * Dmax * 3 * 8;                  // lines
+    b += (size_t)nwarps * Dmax * 8 * 2;             // wa, wb
+    b += lsap_state_bytes(Dmax, Dmax * Dmax);
+    b += (size_t)Dmax * 4 * 6;                      // rm.cmin, rlo, cnt, mcost, mr, mk
+    b += (size_t)nwarps * Dmax * 2 * 2;             // wil, wjl
+    b += (size_t)6 * Dmax;                          // lvalid
+    return (b + 64 + 15) & ~(size_t)15;
+}
+
+__device__ void match_carve(MatchSmem& ms, unsigned char* p, int Dmax, int nwarps) {
+    ms.F = (double*)p; p += 27 * 8;
+    ms.Pm = (double*)p; p += 36 * 8;
+    ms.sc.pts = (double*)p; p += (size_t)3 * Dmax * 2 * 8;
+    ms.sc.lines = (double*)p; p += (size_t)6 * Dmax * 3 * 8;
+    ms.wa = (double*)p; p += (size_t)nwarps * Dmax * 8;
+    ms.wb = (double*)p; p += (size_t)nwarps * Dmax * 8;
+    p = lsap_state_carve(ms.st, p, Dmax, Dmax * Dmax);
+    ms.rm.cmin = (float*)p; p += (size_t)Dmax * 4;
+    ms.rm.rlo = (int*)p; p += (size_t)Dmax * 4;
+    ms.rm.cnt = (int*)p; p += (size_t)Dmax * 4;
+    ms.mcost = (float*)p; p += (size_t)Dmax * 4;
+    ms.mr = (int*)p; p += (size_t)Dmax * 4;
+    ms.mk = (int*)p; p += (size_t)Dmax * 4;
+    ms.wil = (short*)p; p += (size_t)nwarps * Dmax * 2;
+    ms.wjl = (short*)p; p += (size_t)nwarps * Dmax * 2;
+    ms.sc.lvalid = (uint8_t*)p;
+    ms.sc.Dmax = Dmax;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// PoseEstimator._match for one scene per CTA
+// ------------------------------------------------------------------------------------------------------
+__global__ void bpc_match_kernel(const float* __restrict__ Ks, const double* __restrict__ RTs,
+                                 const double* __restrict__ centers, const int32_t* __restrict__ counts,
+                                 int S, int Dmax, float threshold,
+                                 int32_t* __restrict__ idx, int32_t* __restrict__ nout, float* __restrict__ costout,
+                                 double* __restrict__ Xout, double* __restrict__ reproj, double* __restrict__ Fout) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nth = blockDim.x, nwarps = nth >> 5;
+    MatchSmem ms;
+    match_carve(ms, smem_raw, Dmax, nwarps);
+    const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+
+    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        __syncthreads();                                   // previous scene fully written out
+        Scene& sc = ms.sc;
+        sc.N = counts[s * 3 + 0]; sc.M = counts[s * 3 + 1]; sc.P = counts[s * 3 + 2];
+        const float* K = Ks + (size_t)s * 27;
+        const double* RT = RTs + (size_t)s * 48;
+        // ---- phase 0 ---------------------------------------------------------------------------------
+        if (tid < 3) {
+            const int a = (tid == 2) ? 1 : 0, b = (tid == 0) ? 1 : 2;        // pairs 12, 13, 23
+            fundamental(K + a * 9, RT + a * 16, K + b * 9, RT + b * 16, ms.F + tid * 9);
+        } else if (tid >= 32 - 3 && tid < 32) {
+            const int c = tid - (32 - 3);
+            projection(K + c * 9, RT + c * 16, ms.Pm + c * 12);
+        }
+        __syncthreads();
+        if (Fout != nullptr && tid < 27) Fout[(size_t)s * 27 + tid] = ms.F[tid];
+        const int N = sc.N, M = sc.M, P = sc.P;
+        // padding of the outputs
+        for (int e = tid; e < Dmax; e += nth) {
+            idx[((size_t)s * Dmax + e) * 3 + 0] = -1; idx[((size_t)s * Dmax + e) * 3 + 1] = -1; idx[((size_t)s * Dmax + e) * 3 + 2] = -1;
+            costout[(size_t)s * Dmax + e] = __int_as_float(0x7fc00000);
+            for (int c = 0; c < 3; ++c) {
+                Xout[((size_t)s * Dmax + e) * 3 + c] = NaN;
+                if (reproj != nullptr) reproj[((size_t)s * Dmax + e) * 3 + c] = NaN;
+            }
+        }
+        if (N <= 0 || M <= 0 || P <= 0 || N > Dmax || M > Dmax || P > Dmax) {   // process_pose.py:161-163
+            if (tid == 0) nout[s] = 0;
+            continue;
+        }
+        scene_load(sc, ms.F, centers + (size_t)s * 3 * Dmax * 2, nth, tid);
+        const int NM = N * M;
+        const int transposed = NM > P;                       // SciPy: transpose iff more rows than columns
+        const int nr = transposed ? P : NM, nc = transposed ? NM : P;
+        lsap_reset(ms.st, nr, nc, nth, tid);
+        __syncthreads();
+        // ---- phase 1 ---------------------------------------------------------------------------------
+        if (transposed) {
+            const int w = warp_id();
+            for (int k = w; k < P; k += nwarps)
+                row_argmin(sc, k, ms.wa + (size_t)w * Dmax, ms.wb + (size_t)w * Dmax,
+                           ms.wil + (size_t)w * Dmax, ms.wjl + (size_t)w * Dmax, ms.rm);
+        }
+        __syncthreads();
+        // ---- phase 2 ---------------------------------------------------------------------------------
+        VirtualCost acc;
+        acc.sc = &sc; acc.transposed = transposed;
+        LsapState& st = ms.st;
+        int row = 0;
+        for (;;) {
+            if (tid == 0) {
+                int r = row;
+                if (transposed) {
+                    // an unassigned unique argmin column is an immediate sink: every other column has a
+                    // strictly larger cost and v <= 0, so its reduced cost is strictly larger
+                    while (r < nr && ms.rm.cnt[r] == 1 && !st.assigned(ms.rm.rlo[r])) {
+                        const int col = ms.rm.rlo[r];
+                        st.col4row[r] = col; st.vcol[r] = 0.0; st.set_assigned(col);
+                        st.u[r] = (double)ms.rm.cmin[r];
+                        ++r;
+                    }
+                }
+                st.ctl[0] = r;
+            }
+            __syncthreads();
+            row = st.ctl[0];
+            if (row >= nr) break;
+            lsap_augment(st, acc, row, nth, tid);
+            if (st.ctl[2]) break;
+            ++row;
+        }
+        __syncthreads();
+        if (st.ctl[2]) {                                     // infeasible (NaN / inf costs): SciPy raises
+            if (tid == 0) nout[s] = -1;
+            continue;
+        }
+        // ---- phase 3 ---------------------------------------------------------------------------------
+        for (int rrow = tid; rrow < nr; rrow += nth) {
+            const int col = st.col4row[rrow];
+            const int r = transposed ? col : rrow, k = transposed ? rrow : col;
+            const int i = r / M, j = r - i * M;
+            const float c = sc.cost(i, j, k);
+            ms.mcost[rrow] = c; ms.mr[rrow] = (c < threshold) ? r : -1; ms.mk[rrow] = k;
+        }
+        __syncthreads();
+        int kept = 0;
+        for (int e = 0; e < nr; ++e) kept += (ms.mr[e] >= 0);
+        if (tid == 0) nout[s] = kept;
+        for (int rrow = tid; rrow < nr; rrow += nth) {
+            const int r = ms.mr[rrow];
+            if (r < 0) continue;
+            const float c = ms.mcost[rrow];
+            int rank = 0;
+            for (int e = 0; e < nr; ++e) {
+                const int re = ms.mr[e];
+                if (re < 0) continue;
+                const float ce = ms.mcost[e];
+                rank += (ce < c) || (ce == c && re < r);
+            }
+            const int k = ms.mk[rrow];
+            const int i = r / M, j = r - i * M;
+            const size_t o = (size_t)s * Dmax + rank;
+            idx[o * 3 + 0] = i; idx[o * 3 + 1] = j; idx[o * 3 + 2] = k;
+            costout[o] = c;
+            double xy[6];
+            xy[0] = sc.pt(0, i)[0]; xy[1] = sc.pt(0, i)[1];
+            xy[2] = sc.pt(1, j)[0]; xy[3] = sc.pt(1, j)[1];
+            xy[4] = sc.pt(2, k)[0]; xy[5] = sc.pt(2, k)[1];
+            double X[3];
+            triangulate3(ms.Pm, xy, X);
+            Xout[o * 3 + 0] = X[0]; Xout[o * 3 + 1] = X[1]; Xout[o * 3 + 2] = X[2];
+            if (reproj != nullptr)
+                for (int v = 0; v < 3; ++v) reproj[o * 3 + v] = reprojection(ms.Pm + v * 12, X, xy + v * 2);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// match_objects on an explicit cost tensor (epipolar_matching.py:100-116), one CTA per problem
+// ------------------------------------------------------------------------------------------------------
+__global__ void bpc_match_objects_kernel(const float* __restrict__ cost, int S, int N, int M, int P, float threshold,
+                                         int32_t* __restrict__ idx, int32_t* __restrict__ nout) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int NM = N * M;
+    const int transposed = NM > P;
+    const int nr = transposed ? P : NM, nc = transposed ? NM : P;
+    LsapState st;
+    unsigned char* p = lsap_state_carve(st, smem_raw, nr, nc);
+    int* keep = (int*)p;                                    // [nr]
+    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        __syncthreads();
+        lsap_reset(st, nr, nc, nth, tid);
+        __syncthreads();
+        ExplicitCost acc;
+        acc.c = cost + (size_t)s * NM * P; acc.P = P; acc.transposed = transposed;
+        bool bad = false;
+        for (int row = 0; row < nr; ++row) {
+            lsap_augment(st, acc, row, nth, tid);
+            if (st.ctl[2]) { bad = true; break; }
+        }
+        __syncthreads();
+        for (int e = tid; e < nr; e += nth) {
+            idx[((size_t)s * nr + e) * 3 + 0] = -1; idx[((size_t)s * nr + e) * 3 + 1] = -1; idx[((size_t)s * nr + e) * 3 + 2] = -1;
+        }
+        if (bad) {
+            if (tid == 0) nout[s] = -1;
+            continue;
+        }
+        for (int rrow = tid; rrow < nr; rrow += nth) {
+            const int col = st.col4row[rrow];
+            const int r = transposed ? col : rrow, k = transposed ? rrow : col;
+            keep[rrow] = (acc.c[(size_t)r * P + k] < threshold) ? r : -1;
+        }
+        __syncthreads();
+        int kept = 0;
+        for (int e = 0; e < nr; ++e) kept += (keep[e] >= 0);
+        if (tid == 0) nout[s] = kept;
+        for (int rrow = tid; rrow < nr; rrow += nth) {
+            const int r = keep[rrow];
+            if (r < 0) continue;
+            int rank = 0;                                    // ascending r (SciPy's output order)
+            for (int e = 0; e < nr; ++e) rank += (keep[e] >= 0 && keep[e] < r);
+            const int k = transposed ? rrow : st.col4row[rrow];
+            const size_t o = (size_t)s * nr + rank;
+            idx[o * 3 + 0] = r / M; idx[o * 3 + 1] = r % M; idx[o * 3 + 2] = k;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// small stand-alone kernels
+// ------------------------------------------------------------------------------------------------------
+__global__ void bpc_fundamental_kernel(const float* __restrict__ Ks, const double* __restrict__ RTs, int S, double* __restrict__ F) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= S * 3) return;
+    const int s = t / 3, pr = t - s * 3;
+    const int a = (pr == 2) ? 1 : 0, b = (pr == 0) ? 1 : 2;
+    double f[9];
+    fundamental(Ks + (size_t)s * 27 + a * 9, RTs + (size_t)s * 48 + a * 16, Ks + (size_t)s * 27 + b * 9,
+                RTs + (size_t)s * 48 + b * 16, f);
+    for (int e = 0; e < 9; ++e) F[(size_t)t * 9 + e] = f[e];
+}
+
+__global__ void bpc_cost_tensor_kernel(const double* __restrict__ F, const double* __restrict__ centers,
+                                       const int32_t* __restrict__ counts, int S, int Dmax, float* __restrict__ cost) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    double* Fs = (double*)smem_raw;
+    Scene sc;
+    sc.pts = Fs + 27 + 1;
+    sc.lines = sc.pts + (size_t)3 * Dmax * 2;
+    sc.lvalid = (uint8_t*)(sc.lines + (size_t)6 * Dmax * 3);
+    sc.Dmax = Dmax;
+    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        __syncthreads();
+        if (tid < 27) Fs[tid] = F[(size_t)s * 27 + tid];
+        sc.N = counts[s * 3 + 0]; sc.M = counts[s * 3 + 1]; sc.P = counts[s * 3 + 2];
+        __syncthreads();
+        if (sc.N < 0 || sc.M < 0 || sc.P < 0 || sc.N > Dmax || sc.M > Dmax || sc.P > Dmax) continue;
+        scene_load(sc, Fs, centers + (size_t)s * 3 * Dmax * 2, nth, tid);
+        __syncthreads();
+        const int N = sc.N, M = sc.M, P = sc.P;
+        const long long total = (long long)N * M * P;
+        for (long long e = tid; e < total; e += nth) {
+            const int k = (int)(e % P);
+            const int r = (int)(e / P);
+            const int i = r / M, j = r - i * M;
+            cost[(((size_t)s * Dmax + i) * Dmax + j) * Dmax + k] = sc.cost(i, j, k);
+        }
+    }
+}
+
+__global__ void bpc_triangulate_kernel(const double* __restrict__ P, const double* __restrict__ pts, int n, double* __restrict__ X) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double Pm[36], xy[6], x[3];
+    for (int e = 0; e < 36; ++e) Pm[e] = P[(size_t)t * 36 + e];
+    for (int e = 0; e < 6; ++e) xy[e] = pts[(size_t)t * 6 + e];
+    triangulate3(Pm, xy, x);
+    X[(size_t)t * 3 + 0] = x[0]; X[(size_t)t * 3 + 1] = x[1]; X[(size_t)t * 3 + 2] = x[2];
+}
+
+__global__ void bpc_reproj_kernel(const double* __restrict__ P, const double* __restrict__ X, const double* __restrict__ pts,
+                                  int n, double* __restrict__ err) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 3) return;
+    const int m = t / 3;
+    double Pm[12];
+    for (int e = 0; e < 12; ++e) Pm[e] = P[(size_t)t * 12 + e];
+    err[t] = reprojection(Pm, X + (size_t)m * 3, pts + (size_t)t * 2);
+}
+
+__global__ void bpc_box_centers_kernel(const int32_t* __restrict__ boxes, int count, double* __restrict__ centers) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int4 b = reinterpret_cast<const int4*>(boxes)[t];
+    // 0.5 * (x1 + x2) on Python ints (process_pose.py:135-136): the integer sum is exact
+    centers[(size_t)t * 2 + 0] = 0.5 * (double)((long long)b.x + (long long)b.z);
+    centers[(size_t)t * 2 + 1] = 0.5 * (double)((long long)b.y + (long long)b.w);
+}
+
+// ROI records: single CTA exclusive scan over 3*n[s], then a grid-stride fill.
+__global__ void bpc_roi_offsets_kernel(const int32_t* __restrict__ n, int S, int32_t* __restrict__ offs) {
+    __shared__ int part[1024];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int per = (S + nth - 1) / nth;
+    const int lo = min(S, tid * per), hi = min(S, lo + per);
+    int sum = 0;
+    for (int s = lo; s < hi; ++s) sum += 3 * max(0, n[s]);
+    part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int t = 0; t < nth; ++t) { const int v = part[t]; part[t] = acc; acc += v; }
+        offs[S] = acc;
+    }
+    __syncthreads();
+    int acc = part[tid];
+    for (int s = lo; s < hi; ++s) { offs[s] = acc; acc += 3 * max(0, n[s]); }
+}
+
+__global__ void bpc_roi_fill_kernel(const int32_t* __restrict__ boxes, const int32_t* __restrict__ idx, const int32_t* __restrict__ n,
+                                    const int32_t* __restrict__ image_of_scene, int S, int Dmax, int Kmax,
+                                    const int32_t* __restrict__ offs, int32_t* __restrict__ rois) {
+    const long long total = (long long)S * Kmax * 3;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(e % 3);
+        const int m = (int)((e / 3) % Kmax);
+        const int s = (int)(e / (3LL * Kmax));
+        if (m >= n[s]) continue;
+        const int d = idx[((size_t)s * Kmax + m) * 3 + v];
+        const int32_t* b = boxes + (((size_t)s * 3 + v) * Dmax + d) * 4;
+        int32_t* o = rois + ((size_t)offs[s] + (size_t)m * 3 + v) * 5;
+        o[0] = image_of_scene[s * 3 + v]; o[1] = b[0]; o[2] = b[1]; o[3] = b[2]; o[4] = b[3];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host launchers (C ABI)
+// ------------------------------------------------------------------------------------------------------
+static int pick_threads(int Dmax) {
+    if (Dmax <= 32) return 32;
+    if (Dmax <= 64) return 128;
+    return 256;
+}
+
+}  // namespace bpc
+
+using namespace bpc;
+
+extern "C" int bpc_fundamental(const float* Ks, const double* RTs, int S, double* F, void* stream) {
+    if (S < 0 || (S > 0 && (!Ks || !RTs || !F))) return BPC_EINVAL;
+    if (S == 0) return BPC_OK;
+    bpc_fundamental_kernel<<<(S * 3 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(Ks, RTs, S, F);
+    BPC_LAUNCH_CHECK();
+    return BPC_OK;
+}
+
+extern "C" int bpc_cost_tensor(const double* F, const double* centers, const int32_t* counts, int S, int Dmax,
+                               float* cost, void* stream) {
+    if (S < 0 || Dmax < 1 || (S > 0 && (!F || !centers || !counts || !cost))) return BPC_EINVAL;
+    if (Dmax > BPC_MAX_DET) return BPC_ETOOBIG;
+    if (S == 0) return BPC_OK;
+    const size_t smem = (28 + (size_t)3 * Dmax * 2 + (size_t)6 * Dmax * 3) * 8 + (size_t)6 * Dmax + 16;
+    if (smem > 227 * 1024) return BPC_ETOOBIG;
+    cudaError_t e = cudaFuncSetAttribute(bpc_cost_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    bpc_cost_tensor_kernel<<<S, 256, smem, (cudaStream_t)stream>>>(F, centers, counts, S, Dmax, cost);
+    BPC_LAUNCH_CHECK();
+    return BPC_OK;
+}
+
+extern "C" size_t bpc_match_objects_workspace_bytes(int, int, int, int) { return 0; }
+
+extern "C" int bpc_match_objects(const float* cost, int S, int N, int M, int P, float threshold,
+                                 int32_t* idx, int32_t* n, void*, size_t, void* stream) {
+    if (S < 0 || N < 1 || M < 1 || P < 1 || (S > 0 && (!cost || !idx || !n))) return BPC_EINVAL;
+    if ((long long)N * M > (1 << 24) || P > (1 << 24)) return BPC_ETOOBIG;
+    if (S == 0) return BPC_OK;
+    const int NM = N * M;
+    const int nr = NM > P ? P : NM, nc = NM > P ? NM : P;
+    const size_t smem = lsap_state_bytes(nr, nc) + (size_t)nr * 4 + 32;
+    if (smem > 227 * 1024) return BPC_ETOOBIG;
+    cudaError_t e = cudaFuncSetAttribute(bpc_match_objects_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int threads = nc <= 1024 ? 32 : (nc <= 8192 ? 128 : 256);
+    bpc_match_objects_kernel<<<S, threads, smem, (cudaStream_t)stream>>>(cost, S, N, M, P, threshold, idx, n);
+    BPC_LAUNCH_CHECK();
+    return BPC_OK;
+}
+
+extern "C" size_t bpc_match_workspace_bytes(int, int) { return 0; }
+
+extern "C" int bpc_match_triangulate(const float* Ks, const double* RTs, const double* centers, const int32_t* counts,
+                                     int S, int Dmax, float threshold, int32_t* idx, int32_t* n, float* cost, double* X,
+                                     double* reproj, double* F, void*, size_t, void* stream) {
+    if (S < 0 || Dmax < 1) return BPC_EINVAL;
+    if (S > 0 && (!Ks || !RTs || !centers || !counts || !idx || !n || !cost || !X)) return BPC_EINVAL;
+    if (Dmax > BPC_MAX_DET) return BPC_ETOOBIG;
+    if (S == 0) return BPC_OK;
+    int threads = pick_threads(Dmax);
+    size_t smem = match_smem_bytes(Dmax, threads / 32);
+    while (smem > 227 * 1024 && threads > 32) { threads /= 2; smem = match_smem_bytes(Dmax, threads / 32); }
+    if (smem > 227 * 1024) return BPC_ETOOBIG;
+    cudaError_t e = cudaFuncSetAttribute(bpc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    bpc_match_kernel<<<S, threads, smem, (cudaStream_t)stream>>>(Ks, RTs, centers, counts, S, Dmax, threshold, idx, n, cost, X, reproj, F);
+    BPC_LAUNCH_CHECK();
+    return BPC_OK;
+}
+
+extern "C" int bpc_triangulate(const double* P, const double* pts, int n, double* X, void* stream) {
+    if (n < 0 || (n > 0 && (!P || !pts || !X))) return BPC_EINVAL;
+    if (n == 0) return BPC_OK;
+    bpc_triangulate_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(P, pts, n, X);
+    BPC_LAUNCH_CHECK();
+    return BPC_OK;
+}
+
+extern "C" int bpc_reprojection_error(const double* P, const double* X, const double* pts, int n, double* err, void* stream) {
+    if (n < 0 || (n > 0 && (!P || !pts || !X || !err))) return BPC_EINVAL;
+    if (n == 0) return BPC_OK;
+    bpc_reproj_kernel<<<(n * 3 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, X, pts, n, err);
+    BPC_LAUNCH_CHECK();
+    return BPC_OK;
+}
+
+extern "C" int bpc_box_centers(const int32_t* boxes, int count, double* centers, void* stream) {
+    if (count < 0 || (count > 0 && (!boxes || !centers))) return BPC_EINVAL;
+    if (((uintptr_t)boxes & 15) != 0) return BPC_EALIGN;
+    if (count == 0) return BPC_OK;
+    bpc_box_centers_kernel<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(boxes, count, centers);
+    BPC_LAUNCH_CHECK();
+    return BPC_OK;
+}
+
+extern "C" int bpc_build_rois(const int32_t* boxes, const int32_t* idx, const int32_t* n, const int32_t* image_of_scene,
+                              int S, int Dmax, int Kmax, int32_t* scene_offset, int32_t* rois, void* stream) {
+    if (S < 0 || Dmax < 1 || Kmax < 1) return BPC_EINVAL;
+    if (S > 0 && (!boxes || !idx || !n || !image_of_scene || !scene_offset || !rois)) return BPC_EINVAL;
+    if (S == 0) return BPC_OK;
+    bpc_roi_offsets_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, S, scene_offset);
+    BPC_LAUNCH_CHECK();
+    const long long total = (long long)S * Kmax * 3;
+    const int blocks = (int)((total + 255) / 256 > 148 * 8 ? 148 * 8 : (total + 255) / 256);
+    bpc_roi_fill_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(boxes, idx, n, image_of_scene, S, Dmax, Kmax, scene_offset, rois);
+    BPC_LAUNCH_CHECK();
+    return BPC_OK;
+}

@@ -1,0 +1,167 @@
+/*
+ * bpc_b200.h -- C ABI of libbpc_b200.so: the B200 (sm_100a) implementation of the bpc_baseline
+ * multi-camera match + ROI-crop hot path.
+ *
+ * The reference (yatpor/bpc_baseline) is pure Python and has no FFI layer; its boundary for this
+ * path is the Python function surface of bpc/inference/{epipolar_matching,process_pose}.py,
+ * bpc/inference/utils/{camera_utils,triangulation}.py and bpc/utils/data_utils.py.  Each entry
+ * point below names the reference function (file:line) it replaces; INTEGRATION.md shows the
+ * ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless marked "host"; buffers are dense, row-major;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - calls are asynchronous and stream-ordered: no allocation, no synchronisation, no host
+ *     read-back inside the library; workspaces are supplied by the caller;
+ *   - return value: BPC_OK, a negative BPC_E* argument error, or a positive cudaError_t.
+ *
+ * Batched scene layout (S scenes, 3 cameras, at most Dmax detections per camera):
+ *   Ks      float   [S][3][3][3]     intrinsics                      camera_utils.py:16
+ *   RTs     double  [S][3][4][4]     world->camera, f32 values widened, data_utils.py:383-387
+ *   centers double  [S][3][Dmax][2]  detection centres 'bb_center'   process_pose.py:135-136
+ *   boxes   int32   [S][3][Dmax][4]  (x1,y1,x2,y2) 'bbox'            process_pose.py:134
+ *   counts  int32   [S][3]           detections per camera (ragged N, M, P)
+ */
+#ifndef BPC_B200_H
+#define BPC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BPC_ABI_VERSION 1
+
+enum {
+    BPC_OK = 0,
+    BPC_EINVAL = -1,     /* bad size / null pointer / unsupported value */
+    BPC_EALIGN = -2,     /* pointer not aligned as documented */
+    BPC_EWORKSPACE = -3, /* workspace too small */
+    BPC_ETOOBIG = -4     /* problem exceeds a documented limit (Dmax, ROI width) */
+};
+
+/* limits */
+#define BPC_MAX_DET 384         /* Dmax <= 384 detections per camera (shared-memory resident scene) */
+#define BPC_MAX_ROI_WIDTH 8192  /* widest source box the crop kernel stages in shared memory */
+
+int bpc_abi_version(void);
+/* Static string for a code returned by any entry point (host pointer, never freed). */
+const char* bpc_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * a1. Fundamental matrices F12, F13, F23 of every scene.
+ * Replaces compute_fundamental_matrix, bpc/inference/utils/camera_utils.py:23-46, as called
+ * three times by PoseEstimator._match, bpc/inference/process_pose.py:154-159.
+ *   F  double [S][3][3][3]   (pair order 12, 13, 23; F_ab maps a cam-a point to its cam-b line)
+ */
+int bpc_fundamental(const float* Ks, const double* RTs, int S, double* F, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a2-a4. Materialised N x M x P cost tensor (small D / tests; the matcher never builds it).
+ * Replaces compute_cost_matrix, bpc/inference/epipolar_matching.py:83-98 (epipolar_error :5-28,
+ * epipolar_error_full :73-81).
+ *   F     double [S][3][3][3]   from bpc_fundamental (or any caller-supplied F12,F13,F23)
+ *   cost  float  [S][Dmax][Dmax][Dmax]; entries beyond (N,M,P) of a scene are left untouched
+ */
+int bpc_cost_tensor(const double* F, const double* centers, const int32_t* counts, int S, int Dmax,
+                    float* cost, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a5. Thresholded rectangular assignment on an explicit cost tensor.
+ * Replaces match_objects, bpc/inference/epipolar_matching.py:100-116 (scipy
+ * linear_sum_assignment on cost.reshape(N*M, P), keep cost < threshold, ascending r = i*M+j).
+ *   cost       float [S][N][M][P]          dense, same N, M, P for the whole batch
+ *   idx        int32 [S][Kmax][3]          (i, j, k) per kept match, ascending r, -1 padded
+ *   n          int32 [S]                   kept matches per scene
+ *   Kmax       = min(N*M, P)
+ * Workspace: bpc_match_objects_workspace_bytes(S, N, M, P).
+ */
+size_t bpc_match_objects_workspace_bytes(int S, int N, int M, int P);
+int bpc_match_objects(const float* cost, int S, int N, int M, int P, float threshold,
+                      int32_t* idx, int32_t* n, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a1-a10. The whole geometry path of PoseEstimator._match, bpc/inference/process_pose.py:144-188,
+ * for S independent scenes: fundamental matrices, virtual cost tensor, assignment, threshold,
+ * stable sort by cost (:183), DLT triangulation of every match (PosePrediction :79-94,
+ * triangulate_multi_view epipolar_matching.py:118-127) and per-view reprojection error
+ * (compute_reprojection_error, bpc/inference/utils/triangulation.py:14-18).
+ *   threshold  compared as float32 against the float32 cost (epipolar_matching.py:110-111)
+ *   Kmax       = Dmax
+ *   idx    int32  [S][Kmax][3]  matches sorted by (cost, r); -1 padded
+ *   n      int32  [S]           matches per scene (0 if any camera has no detection, :161-163)
+ *   cost   float  [S][Kmax]     cost of each match (NaN padded)
+ *   X      double [S][Kmax][3]  triangulated points (NaN padded)
+ *   reproj double [S][Kmax][3]  reprojection error per view, pixels (NaN padded); may be NULL
+ *   F      double [S][3][3][3]  fundamental matrices; may be NULL
+ * Workspace: bpc_match_workspace_bytes(S, Dmax) (may be 0).
+ */
+size_t bpc_match_workspace_bytes(int S, int Dmax);
+int bpc_match_triangulate(const float* Ks, const double* RTs, const double* centers, const int32_t* counts,
+                          int S, int Dmax, float threshold,
+                          int32_t* idx, int32_t* n, float* cost, double* X, double* reproj, double* F,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a8. Stand-alone DLT triangulation.  Replaces triangulate_multi_view,
+ * bpc/inference/epipolar_matching.py:118-127 (= utils/triangulation.py:3-12) for 3 views.
+ *   P    double [n][3][3][4]   projection matrices
+ *   pts  double [n][3][2]      image points
+ *   X    double [n][3]
+ * a9. Reprojection error, bpc/inference/utils/triangulation.py:14-18.
+ *   err  double [n][3]
+ */
+int bpc_triangulate(const double* P, const double* pts, int n, double* X, void* stream);
+int bpc_reprojection_error(const double* P, const double* X, const double* pts, int n, double* err, void* stream);
+
+/* Centres from integer boxes: cx = 0.5*(x1+x2), cy = 0.5*(y1+y2), process_pose.py:134-136. */
+int bpc_box_centers(const int32_t* boxes, int count, double* centers, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ROI records for the crop kernel from the matcher's output: 3 per match in (scene, match, view)
+ * order, rois int32 [R][5] = (image index, x1, y1, x2, y2).  Mirrors the loops of
+ * PoseEstimator._estimate_rotation, process_pose.py:195-201.
+ *   image_of_scene int32 [S][3]     index of each view's image in the image pool
+ *   scene_offset   int32 [S + 1]    exclusive prefix sum of 3*n (output; scene_offset[S] = R)
+ *   rois           int32 [S*Kmax*3][5] capacity
+ */
+int bpc_build_rois(const int32_t* boxes, const int32_t* idx, const int32_t* n, const int32_t* image_of_scene,
+                   int S, int Dmax, int Kmax, int32_t* scene_offset, int32_t* rois, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a11 + a12. Crop -> letterbox (INTER_AREA) -> colour order -> /255 -> normalise, for R ROIs.
+ * Replaces letterbox_preserving_aspect_ratio, bpc/utils/data_utils.py:34-44, and the inline
+ * transform of PoseEstimator._estimate_rotation, bpc/inference/process_pose.py:199-209
+ * (training twin: data_utils.py:243-252,282 = swap_rb 0).
+ *   images   uint8 [B][H][W][3]   BGR, 16-byte aligned base
+ *   rois     int32 [R][5]         (image, x1, y1, x2, y2), 0 <= x1 < x2 <= W, 0 <= y1 < y2 <= H
+ *   n_rois_dev  optional device int32: number of valid ROIs (<= R); NULL = all R
+ *   T        target size (reference default 256)
+ *   fill     host uint8[3], letterbox colour in source channel order
+ *   swap_rb  1 = BGR->RGB as cv2.cvtColor(COLOR_BGR2RGB) at process_pose.py:206
+ *   lut      float [3][256]: lut[c][v] = normalised value of byte v in OUTPUT channel c
+ *   out      float [R][3][T][T]   (16-byte aligned)
+ *   status   optional int32 [R]: 0 ok, 1 = ROI rejected (empty box, resized side < 1, out of
+ *            image, wider than BPC_MAX_ROI_WIDTH); a rejected ROI's output is all fill colour
+ * bpc_roi_crop_u8 writes the uint8 letterboxed image itself, uint8 [R][T][T][3] in source channel
+ * order -- exactly what letterbox_preserving_aspect_ratio returns.
+ */
+int bpc_roi_crop(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R,
+                 const int32_t* n_rois_dev, int T, const uint8_t* fill, int swap_rb, const float* lut,
+                 float* out, int32_t* status, void* stream);
+int bpc_roi_crop_u8(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R,
+                    const int32_t* n_rois_dev, int T, const uint8_t* fill,
+                    uint8_t* out, int32_t* status, void* stream);
+/* lut[c][v] = (v/255 - mean[c]) / std[c] in float32 with true divisions, as torchvision's
+ * to_tensor (.div(255)) + normalize (.sub_(mean).div_(std)); process_pose.py:207-209. */
+int bpc_normalise_lut(const float* mean_host3, const float* std_host3, float* lut, void* stream);
+
+/* Number of kernel launches issued by this library since load (all entry points). */
+unsigned long long bpc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BPC_B200_H */

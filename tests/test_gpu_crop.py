@@ -1,0 +1,112 @@
+"""CUDA ROI-crop path (through the C ABI) against the reference's own letterbox outputs and cv2.
+
+Bar: crops within 1e-3 absolute in normalised units; 1 uint8 LSB is 0.017 there, so the uint8 resize
+must be, and is asserted to be, bit-exact; the float tensor is asserted bit-equal to torchvision's.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import crop as ocrop
+from tests.gpu_util import to_dev
+
+pytestmark = pytest.mark.gpu
+
+
+def _rois(boxes, img=0):
+    return np.concatenate([np.full((len(boxes), 1), img, np.int32), np.asarray(boxes, np.int32)], axis=1)
+
+
+@pytest.mark.parametrize('T', [224, 256, 64])
+def test_letterbox_u8_golden(golden_crops, T):
+    from bpc_baseline_b200 import batched
+    g = golden_crops
+    boxes = g['boxes'] if T != 256 else g['boxes'][::2]
+    images = to_dev(g['image'][None])
+    status = torch.zeros(len(boxes), dtype=torch.int32, device='cuda')
+    out = batched.roi_crop_u8(images, to_dev(_rois(boxes)), T=T, status=status).cpu().numpy()
+    assert int(status.sum()) == 0
+    for r, b in enumerate(boxes):
+        diff = out[r].astype(int) - g[f'canvas_T{T}'][r]
+        assert not diff.any(), (T, tuple(b), int(np.abs(diff).max()), int((diff != 0).sum()))
+
+
+def test_tensor_golden_and_lut(golden_crops):
+    from bpc_baseline_b200 import batched
+    g = golden_crops
+    lut = batched.normalise_lut('cuda').cpu().numpy()
+    assert np.array_equal(lut.view(np.uint32), g['lut'].view(np.uint32))
+    images = to_dev(g['image'][None])
+    out = batched.roi_crop(images, to_dev(_rois(g['boxes'][:4])), T=64, swap_rb=True).cpu().numpy()
+    assert np.array_equal(out.view(np.uint32), g['tensor_T64'].view(np.uint32))
+
+
+@pytest.mark.parametrize('T,swap', [(224, True), (256, True), (224, False)])
+def test_tensor_vs_reference_calls(golden_crops, T, swap):
+    """f32 [R,3,T,T] against the reference's four library calls (cv2.resize, cvtColor, to_tensor, normalize)."""
+    from bpc_baseline_b200 import batched
+    g = golden_crops
+    boxes = g['boxes']
+    out = batched.roi_crop(to_dev(g['image'][None]), to_dev(_rois(boxes)), T=T, swap_rb=swap).cpu().numpy()
+    for r, b in enumerate(boxes):
+        want = ocrop.crop_tensor_ref(g['image'], b, target_size=T, swap_rb=swap)
+        assert np.abs(out[r] - want).max() <= 1e-3                       # the north-star tolerance
+        assert np.array_equal(out[r].view(np.uint32), want.view(np.uint32)), tuple(b)
+
+
+def test_random_boxes_all_regimes_full_res():
+    """Full-resolution image pool, random boxes U{8..900}, T=224: bit-exact uint8 vs cv2 through the oracle."""
+    from bpc_baseline_b200 import batched, synth
+    from oracle.area_spec import regime
+    imgs = synth.make_images(2, seed=5, width=1920, height=1080)
+    rng = np.random.default_rng(17)
+    rois = []
+    for _ in range(160):
+        w, h = rng.integers(8, 900, 2)
+        x1 = int(rng.integers(0, 1920 - w + 1)); y1 = int(rng.integers(0, 1080 - h + 1))
+        rois.append((int(rng.integers(0, 2)), x1, y1, x1 + int(w), y1 + int(h)))
+    rois += [(1, 0, 0, 1920, 1080), (0, 1919 - 8, 1080 - 9, 1919, 1080), (1, 0, 0, 448, 448), (0, 5, 5, 5 + 672, 5 + 448),
+             (0, 0, 0, 224, 224), (1, 100, 100, 100 + 224, 100 + 112)]
+    rois = np.asarray(rois, np.int32)
+    out = batched.roi_crop_u8(to_dev(imgs), to_dev(rois), T=224).cpu().numpy()
+    seen = set()
+    for r, (b, x1, y1, x2, y2) in enumerate(rois):
+        want = ocrop.crop_u8_ref(imgs[b], (x1, y1, x2, y2), 224)
+        _, nw, nh, _, _ = ocrop.letterbox_geometry(y2 - y1, x2 - x1, 224)
+        seen.add(regime(x2 - x1, y2 - y1, nw, nh))
+        assert np.array_equal(out[r], want), (r, tuple(rois[r]))
+    assert seen == {1, 2, 3}
+
+
+def test_rejected_rois_and_device_count():
+    from bpc_baseline_b200 import batched, synth
+    imgs = to_dev(synth.make_images(1, seed=6, width=640, height=480))
+    rois = np.array([[0, 10, 10, 200, 150], [0, 50, 50, 50, 90], [0, 600, 400, 700, 470], [3, 0, 0, 10, 10],
+                     [0, 0, 0, 640, 1], [0, 20, 30, 120, 140]], np.int32)
+    status = torch.full((6,), -1, dtype=torch.int32, device='cuda')
+    out = batched.roi_crop(imgs, to_dev(rois), T=64, status=status)
+    st = status.cpu().numpy()
+    # empty box, out of image, bad image index, and a box whose short side rounds to 0 (640x1 -> 64x0)
+    assert list(st) == [0, 1, 1, 1, 1, 0]
+    white = batched.normalise_lut('cuda')[:, 255].cpu().numpy()
+    for r in (1, 2, 3, 4):
+        assert np.array_equal(out[r].cpu().numpy(), np.broadcast_to(white[:, None, None], (3, 64, 64)))
+    # device-side ROI count: rows beyond it are not written
+    out2 = torch.full((6, 3, 64, 64), 7.0, device='cuda')
+    batched.roi_crop(imgs, to_dev(rois), T=64, n_rois=torch.tensor([1], dtype=torch.int32, device='cuda'), out=out2)
+    assert torch.equal(out2[0], out[0]) and bool((out2[1:] == 7.0).all())
+
+
+def test_build_rois_matches_host_mirror():
+    from bpc_baseline_b200 import batched, synth
+    from tests.gpu_util import batch_to_dev
+    batch = synth.make_scenes(32, 7, seed=synth.SEED + 21, p_drop=0.2)
+    Ks, RTs, centers, boxes, counts = batch_to_dev(batch)
+    res = batched.match_triangulate(Ks, RTs, centers, counts, 30)
+    ios = np.arange(32 * 3, dtype=np.int32).reshape(32, 3) % 5
+    rois, offs = batched.build_rois(boxes, res.idx, res.n, to_dev(ios))
+    offs = offs.cpu().numpy()
+    want = synth.rois_for_matches(batch.boxes, res.idx.cpu().numpy(), res.n.cpu().numpy(), ios)
+    assert offs[-1] == len(want)
+    assert np.array_equal(rois.cpu().numpy()[:offs[-1]], want)
+    assert np.array_equal(offs[:-1], np.concatenate([[0], np.cumsum(3 * res.n.cpu().numpy())[:-1]]))
