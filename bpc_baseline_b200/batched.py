@@ -196,12 +196,13 @@ def _crop_args(images, rois, T, fill):
 
 
 def roi_crop(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(255, 255, 255), swap_rb: bool = True,
-             lut: Optional[torch.Tensor] = None, n_rois: Optional[torch.Tensor] = None,
+             lut: Optional[torch.Tensor] = None, n_rois: Optional[torch.Tensor] = None, roi_first: int = 0,
              out: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Network inputs f32 [R,3,T,T] for R ROIs (data_utils.py:34-44 + process_pose.py:199-209).
 
-    ``n_rois``: optional device int32 scalar tensor; ROIs at or beyond it are skipped (their output
-    rows are left untouched).  ``status``: optional int32 [R], 1 where an ROI was rejected.
+    ``n_rois``: optional device int32 scalar tensor holding the number of valid ROIs of the whole batch;
+    record r is processed iff ``roi_first + r < n_rois`` (skipped rows of ``out`` are left untouched), so
+    a long ROI list can be processed chunk by chunk into one reusable ``out`` buffer.  ``status``: optional int32 [R], 1 where an ROI was rejected.
     """
     B, H, W, R, f = _crop_args(images, rois, T, fill)
     dev = images.device
@@ -219,13 +220,13 @@ def roi_crop(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(255, 
     if n_rois is not None:
         _chk(n_rois, torch.int32, 'n_rois')
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().bpc_roi_crop(_p(images), B, H, W, _p(rois), R, _p(n_rois), int(T), f, int(bool(swap_rb)),
+        _lib.check(_lib.load().bpc_roi_crop(_p(images), B, H, W, _p(rois), R, _p(n_rois), int(roi_first), int(T), f, int(bool(swap_rb)),
                                             _p(lut), _p(out), _p(status), _stream(dev)), 'bpc_roi_crop')
     return out
 
 
 def roi_crop_u8(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(255, 255, 255),
-                n_rois: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+                   n_rois: Optional[torch.Tensor] = None, roi_first: int = 0, out: Optional[torch.Tensor] = None,
                 status: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Letterboxed uint8 crops [R,T,T,3] in source channel order (data_utils.py:34-44)."""
     B, H, W, R, f = _crop_args(images, rois, T, fill)
@@ -235,6 +236,6 @@ def roi_crop_u8(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(25
     if status is not None:
         _chk(status, torch.int32, 'status', 1)
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().bpc_roi_crop_u8(_p(images), B, H, W, _p(rois), R, _p(n_rois), int(T), f, _p(out), _p(status),
+        _lib.check(_lib.load().bpc_roi_crop_u8(_p(images), B, H, W, _p(rois), R, _p(n_rois), int(roi_first), int(T), f, _p(out), _p(status),
                                                _stream(dev)), 'bpc_roi_crop_u8')
     return out

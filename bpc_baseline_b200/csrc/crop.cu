@@ -89,7 +89,7 @@ __device__ __forceinline__ void linear_coef(int d, double scale, double inv, int
 template <bool OUT_U8>
 __global__ void __launch_bounds__(256)
 bpc_crop_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const int32_t* __restrict__ rois, int R,
-                const int32_t* __restrict__ n_rois_dev, int T, int nbands, uchar4 fill, int swap_rb,
+                const int32_t* __restrict__ n_rois_dev, int roi_first, int T, int nbands, uchar4 fill, int swap_rb,
                 const float* __restrict__ lut_g, float* __restrict__ outf, uint8_t* __restrict__ outb,
                 int32_t* __restrict__ status) {
     extern __shared__ __align__(16) unsigned char raw[];
@@ -100,7 +100,7 @@ bpc_crop_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const i
     const int tid = threadIdx.x, nth = blockDim.x;
     const int roi = blockIdx.x / nbands, band = blockIdx.x - roi * nbands;
     if (roi >= R) return;
-    if (n_rois_dev != nullptr && roi >= *n_rois_dev) return;
+    if (n_rois_dev != nullptr && roi_first + roi >= *n_rois_dev) return;
 
     if (tid == 0) {
         const int32_t* r = rois + (size_t)roi * 5;
@@ -360,7 +360,7 @@ __global__ void bpc_lut_kernel(float m0, float m1, float m2, float s0, float s1,
 
 template <bool OUT_U8>
 static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R, const int32_t* n_rois_dev,
-                       int T, const uint8_t* fill, int swap_rb, const float* lut, float* outf, uint8_t* outb,
+                       int roi_first, int T, const uint8_t* fill, int swap_rb, const float* lut, float* outf, uint8_t* outb,
                        int32_t* status, void* stream) {
     if (R < 0 || B < 1 || H < 1 || W < 1 || T < 1 || T > 256 || !fill) return BPC_EINVAL;
     if (R > 0 && (!images || !rois || (!OUT_U8 && (!lut || !outf)) || (OUT_U8 && !outb))) return BPC_EINVAL;
@@ -376,7 +376,7 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
         attr_set[OUT_U8] = true;
     }
     bpc_crop_kernel<OUT_U8><<<R * nbands, threads, CROP_RAW_BYTES, (cudaStream_t)stream>>>(
-        images, B, H, W, rois, R, n_rois_dev, T, nbands, make_uchar4(fill[0], fill[1], fill[2], 0), swap_rb, lut, outf, outb, status);
+        images, B, H, W, rois, R, n_rois_dev, roi_first, T, nbands, make_uchar4(fill[0], fill[1], fill[2], 0), swap_rb, lut, outf, outb, status);
     BPC_LAUNCH_CHECK();
     return BPC_OK;
 }
@@ -386,16 +386,16 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
 using namespace bpc;
 
 extern "C" int bpc_roi_crop(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R,
-                            const int32_t* n_rois_dev, int T, const uint8_t* fill, int swap_rb, const float* lut,
-                            float* out, int32_t* status, void* stream) {
+                            const int32_t* n_rois_dev, int roi_first, int T, const uint8_t* fill, int swap_rb,
+                            const float* lut, float* out, int32_t* status, void* stream) {
     if (((uintptr_t)out & 15) != 0) return BPC_EALIGN;
-    return launch_crop<false>(images, B, H, W, rois, R, n_rois_dev, T, fill, swap_rb, lut, out, nullptr, status, stream);
+    return launch_crop<false>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, fill, swap_rb, lut, out, nullptr, status, stream);
 }
 
 extern "C" int bpc_roi_crop_u8(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R,
-                               const int32_t* n_rois_dev, int T, const uint8_t* fill, uint8_t* out, int32_t* status,
-                               void* stream) {
-    return launch_crop<true>(images, B, H, W, rois, R, n_rois_dev, T, fill, 0, nullptr, nullptr, out, status, stream);
+                               const int32_t* n_rois_dev, int roi_first, int T, const uint8_t* fill, uint8_t* out,
+                               int32_t* status, void* stream) {
+    return launch_crop<true>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, fill, 0, nullptr, nullptr, out, status, stream);
 }
 
 extern "C" int bpc_normalise_lut(const float* mean, const float* std_, float* lut, void* stream) {

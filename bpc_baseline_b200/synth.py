@@ -167,16 +167,18 @@ def make_images(B: int, *, seed: int = SEED, width: int = IMG_W, height: int = I
     Gradients land on .5 rounding boundaries of the resize far more often than white noise.
     """
     rng = np.random.default_rng([seed, 7777])
-    yy = np.arange(height, dtype=np.float32)[:, None, None]
-    xx = np.arange(width, dtype=np.float32)[None, :, None]
+    yy = np.arange(height, dtype=np.float32)[:, None]
+    xx = np.arange(width, dtype=np.float32)[:, None]
     out = np.empty((B, height, width, 3), np.uint8)
     for b in range(B):
         fx = rng.uniform(0.01, 0.2, 3).astype(np.float32)
         fy = rng.uniform(0.01, 0.2, 3).astype(np.float32)
         ph = rng.uniform(0, 6.28, 3).astype(np.float32)
-        img = 127.5 + 70.0 * np.sin(xx * fx + ph) + 50.0 * np.cos(yy * fy - ph)
-        img += rng.normal(0.0, 6.0, img.shape).astype(np.float32)
-        out[b] = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+        gx = (127.5 + 70.0 * np.sin(xx * fx + ph)).astype(np.float32)       # [W, 3]
+        gy = (50.0 * np.cos(yy * fy - ph)).astype(np.float32)               # [H, 3]
+        img = np.rint(gy[:, None, :] + gx[None, :, :]).astype(np.int16)
+        img += rng.integers(-12, 13, img.shape, dtype=np.int8)
+        out[b] = np.clip(img, 0, 255).astype(np.uint8)
     return out
 
 

@@ -137,7 +137,10 @@ int bpc_build_rois(const int32_t* boxes, const int32_t* idx, const int32_t* n, c
  * (training twin: data_utils.py:243-252,282 = swap_rb 0).
  *   images   uint8 [B][H][W][3]   BGR, 16-byte aligned base
  *   rois     int32 [R][5]         (image, x1, y1, x2, y2), 0 <= x1 < x2 <= W, 0 <= y1 < y2 <= H
- *   n_rois_dev  optional device int32: number of valid ROIs (<= R); NULL = all R
+ *   n_rois_dev  optional device int32 holding the TOTAL number of valid ROIs of the batch the
+ *               records belong to (e.g. scene_offset[S] of bpc_build_rois); NULL = all R are valid
+ *   roi_first   index, within that batch, of rois[0] (chunked processing into a reusable `out`):
+ *               record r is processed iff roi_first + r < *n_rois_dev
  *   T        target size (reference default 256)
  *   fill     host uint8[3], letterbox colour in source channel order
  *   swap_rb  1 = BGR->RGB as cv2.cvtColor(COLOR_BGR2RGB) at process_pose.py:206
@@ -149,10 +152,10 @@ int bpc_build_rois(const int32_t* boxes, const int32_t* idx, const int32_t* n, c
  * order -- exactly what letterbox_preserving_aspect_ratio returns.
  */
 int bpc_roi_crop(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R,
-                 const int32_t* n_rois_dev, int T, const uint8_t* fill, int swap_rb, const float* lut,
-                 float* out, int32_t* status, void* stream);
+                 const int32_t* n_rois_dev, int roi_first, int T, const uint8_t* fill, int swap_rb,
+                 const float* lut, float* out, int32_t* status, void* stream);
 int bpc_roi_crop_u8(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R,
-                    const int32_t* n_rois_dev, int T, const uint8_t* fill,
+                    const int32_t* n_rois_dev, int roi_first, int T, const uint8_t* fill,
                     uint8_t* out, int32_t* status, void* stream);
 /* lut[c][v] = (v/255 - mean[c]) / std[c] in float32 with true divisions, as torchvision's
  * to_tensor (.div(255)) + normalize (.sub_(mean).div_(std)); process_pose.py:207-209. */

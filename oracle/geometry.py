@@ -138,6 +138,44 @@ def cost_tensor(c1, c2, c3, F12, F13, F23):
     return (s / 3).astype(np.float32)
 
 
+def _pair_matrix_fast(pa, pb, F):
+    """_pair_matrix with the D*D dot products batched into two matrix products.
+
+    Lines still come from the reference's per-point calls; only ``np.dot(l, p)`` per pair becomes a
+    row of a (D,3)@(3,D) product.  On the hosts tried the BLAS gemm accumulates the three products in
+    the same fused order as ddot, so the result is bit-identical; ``cost_tensor_fast`` verifies that
+    on its first calls and falls back to ``_pair_matrix`` if it ever is not.
+    """
+    pah = np.concatenate([np.asarray(pa, np.float64), np.ones((len(pa), 1))], axis=1)
+    pbh = np.concatenate([np.asarray(pb, np.float64), np.ones((len(pb), 1))], axis=1)
+    L2 = np.stack([F @ p for p in pah])
+    L1 = np.stack([F.T @ p for p in pbh])
+    n2 = np.array([np.linalg.norm(l[:2]) for l in L2])
+    n1 = np.array([np.linalg.norm(l[:2]) for l in L1])
+    ok2, ok1 = n2 > 1e-8, n1 > 1e-8
+    L2 = np.where(ok2[:, None], L2 / np.where(ok2, n2, 1.0)[:, None], L2)
+    L1 = np.where(ok1[:, None], L1 / np.where(ok1, n1, 1.0)[:, None], L1)
+    d1 = np.where(ok1[None, :], np.abs(pah @ L1.T), 9999.0)
+    d2 = np.where(ok2[:, None], np.abs(L2 @ pbh.T), 9999.0)
+    return 0.5 * (d1 + d2)
+
+
+_FAST_STATE = {'checked': 0, 'ok': True}
+
+
+def cost_tensor_fast(c1, c2, c3, F12, F13, F23):
+    """cost_tensor at NumPy speed (the CPU-baseline workhorse); self-checking, see _pair_matrix_fast."""
+    fn = _pair_matrix_fast if _FAST_STATE['ok'] else _pair_matrix
+    e12, e13, e23 = fn(c1, c2, F12), fn(c1, c3, F13), fn(c2, c3, F23)
+    if _FAST_STATE['ok'] and _FAST_STATE['checked'] < 3:
+        _FAST_STATE['checked'] += 1
+        if not np.array_equal(e12, _pair_matrix(c1, c2, F12)):
+            _FAST_STATE['ok'] = False
+            return cost_tensor(c1, c2, c3, F12, F13, F23)
+    s = (e12[:, :, None] + e13[:, None, :]) + e23[None, :, :]
+    return (s / 3).astype(np.float32)
+
+
 def match_objects(cost_matrix, threshold):
     """Flatten -> SciPy LSAP -> keep cost < threshold -- reference epipolar_matching.py:100-116."""
     N, M, P = cost_matrix.shape
