@@ -28,8 +28,9 @@ SIGNATURES = {
     'bpc_reprojection_error': (_i, [_p, _p, _p, _i, _p, _p]),
     'bpc_box_centers': (_i, [_p, _i, _p, _p]),
     'bpc_build_rois': (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
-    'bpc_roi_crop': (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _i, _p, _p, _p, _p]),
-    'bpc_roi_crop_u8': (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p]),
+    'bpc_roi_crop_workspace_bytes': (_sz, [_i]),
+    'bpc_roi_crop': (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
+    'bpc_roi_crop_u8': (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),
     'bpc_normalise_lut': (_i, [_p, _p, _p, _p]),
 }
 

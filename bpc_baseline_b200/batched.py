@@ -184,6 +184,20 @@ def normalise_lut(device, mean: Sequence[float] = MEAN, std: Sequence[float] = S
     return _LUT_CACHE[key]
 
 
+_WS_CACHE: dict = {}
+
+
+def _crop_workspace(dev, R: int) -> torch.Tensor:
+    """Device scratch for the crop kernels, cached per device and grown on demand."""
+    need = int(_lib.load().bpc_roi_crop_workspace_bytes(int(R)))
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty((max(need, 1 << 16),), dtype=torch.uint8, device=dev)
+        _WS_CACHE[key] = ws
+    return ws
+
+
 def _crop_args(images, rois, T, fill):
     _chk(images, torch.uint8, 'images', 4); _chk(rois, torch.int32, 'rois', 2)
     B, H, W, ch = images.shape
@@ -219,9 +233,10 @@ def roi_crop(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(255, 
         _chk(status, torch.int32, 'status', 1)
     if n_rois is not None:
         _chk(n_rois, torch.int32, 'n_rois')
+    ws = _crop_workspace(dev, R)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().bpc_roi_crop(_p(images), B, H, W, _p(rois), R, _p(n_rois), int(roi_first), int(T), f, int(bool(swap_rb)),
-                                            _p(lut), _p(out), _p(status), _stream(dev)), 'bpc_roi_crop')
+                                            _p(lut), _p(out), _p(status), _p(ws), ws.numel(), _stream(dev)), 'bpc_roi_crop')
     return out
 
 
@@ -235,7 +250,8 @@ def roi_crop_u8(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(25
         out = torch.empty((R, T, T, 3), dtype=torch.uint8, device=dev)
     if status is not None:
         _chk(status, torch.int32, 'status', 1)
+    ws = _crop_workspace(dev, R)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().bpc_roi_crop_u8(_p(images), B, H, W, _p(rois), R, _p(n_rois), int(roi_first), int(T), f, _p(out), _p(status),
-                                               _stream(dev)), 'bpc_roi_crop_u8')
+                                               _p(ws), ws.numel(), _stream(dev)), 'bpc_roi_crop_u8')
     return out

@@ -7,34 +7,45 @@
 //   regime 2  both shrink, integer ratio : integer box sum; 2x2 -> (sum+2)>>2
 //   regime 3  either axis grows          : 11-bit fixed-point bilinear with area-mode coordinates
 //
-// Mapping: one CTA per (ROI, band of BAND output rows); one thread per output column x, all three
-// channels.  The source rows a band needs are staged in shared memory with 128-bit loads of the
-// 16-byte-aligned superset of each row; each thread then streams down its column: the horizontal pass
-// of a source row is computed once and reused by the (at most two) output rows that tap it.
-// The dominant traffic is the float32 output (3*T*T*4 B per ROI): each warp stores 128 contiguous
-// bytes per plane and row.
+// Three kernels per call:
+//   bpc_crop_prep     one thread per ROI: letterbox geometry (float64, as Python / OpenCV compute it),
+//                     regime, and the class of the ROI (fast / generic / rejected / beyond the count);
+//   bpc_crop_fast     one CTA per ROI, one thread per output column.  Handles regime 1 with scale < 2 on
+//                     both axes (at most 3 taps per axis) and regime 3 -- every box whose long side is
+//                     below 2T.  Source rows of a band of output rows are staged in shared memory with
+//                     16-byte cp.async (double buffered), each thread streams down its column: the
+//                     horizontal pass of a source row is computed once and reused by the two output rows
+//                     that tap it; weights of absent taps are +0.0f, which leaves every float32 sum
+//                     bit-identical (x + 0 == x) while keeping the inner loop branch-free;
+//   bpc_crop_generic  persistent CTAs over the (rare) remaining ROIs: any scale, any regime, source rows
+//                     streamed through shared memory in chunks (handles boxes as large as the image).
+// The dominant traffic is the float32 output (3*T*T*4 B per ROI): each warp stores 128 contiguous bytes
+// per plane and row; padding rows are written with 16-byte stores.
 #include "common.cuh"
 
 namespace bpc {
 
-constexpr int CROP_BAND = 8;            // output rows per CTA
-constexpr int CROP_RAW_BYTES = 40 * 1024;
+constexpr int CROP_BAND = 8;                 // generic kernel: output rows per work item
+constexpr int CROP_RAW_BYTES = 40 * 1024;    // generic kernel: staged source bytes
+constexpr int FAST_BUF_BYTES = 20 * 1024;    // fast kernel: one of two staging buffers
+constexpr int FAST_MAX_BAND = 64;
 
-struct RoiGeom {
+struct RoiGeom {                             // 88 bytes, workspace
     double scale_x, scale_y, inv_x, inv_y;
-    unsigned long long src;            // byte address of (y1, x1) in its image
+    unsigned long long src;                  // byte address of (y1, x1) in its image
     int w, h, new_w, new_h, dx, dy;
-    int regime;                        // 0 = rejected, 1 / 2 / 3 as above
+    int regime;                              // 0 rejected, 1 / 2 / 3
+    int cls;                                 // -1 beyond the device count, 0 rejected (all fill), 1 fast area, 3 fast linear, 2 generic
     int isx, isy;
-    int pitch;                         // shared-memory bytes per staged source row (multiple of 16)
-    int rows_fit;
+    int pitch, pad_;
 };
+static_assert(sizeof(RoiGeom) == 88, "RoiGeom layout");
 
-struct YDesc {                         // per output row of the band
-    int start;                         // first source row tapped
-    int n;                             // taps (regime 1/2) ; regime 3: second source row
-    float bf, bm, bl;                  // regime 1 weights ; regime 3: b0, b1 as ints in bf/bm bits
-    int flags;                         // bit0 has_first, bit1 has_last
+struct YDesc {                               // generic kernel, per output row of the band
+    int start;
+    int n;                                   // taps (regime 1/2) ; regime 3: second source row
+    float bf, bm, bl;                        // regime 1 weights ; regime 3: b0, b1 as int bits
+    int flags;                               // bit0 has_first, bit1 has_last
 };
 
 __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
@@ -43,6 +54,12 @@ __device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // computeResizeAreaTab for one destination index d (OpenCV resize.cpp), all in float64.
 __device__ __forceinline__ void area_taps(int d, double scale, int ssize, int& start, int& n, float& af, float& am, float& al, int& flags) {
@@ -70,6 +87,20 @@ __device__ __forceinline__ void area_taps(int d, double scale, int ssize, int& s
     }
 }
 
+// the same taps as a start index and three weights (absent taps = +0.0f); valid when n <= 3 (scale < 2)
+__device__ __forceinline__ void area_taps3(int d, double scale, int ssize, int& start, int& n, float& w0, float& w1, float& w2) {
+    float af, am, al;
+    int flags;
+    area_taps(d, scale, ssize, start, n, af, am, al, flags);
+    float w[3] = {0.f, 0.f, 0.f};
+    int k = 0;
+    if (flags & 1) w[k++] = af;
+    const int m = n - (flags & 1) - ((flags >> 1) & 1);
+    for (int t = 0; t < m && k < 3; ++t) w[k++] = am;
+    if ((flags & 2) && k < 3) w[k++] = al;
+    w0 = w[0]; w1 = w[1]; w2 = w[2];
+}
+
 // area-mode coordinates of the generic linear resize for one destination index d.
 __device__ __forceinline__ void linear_coef(int d, double scale, double inv, int ssize, int& s0, int& w0, int& w1, int& edge) {
     int s = (int)floor(dmul((double)d, scale));
@@ -86,71 +117,75 @@ __device__ __forceinline__ void linear_coef(int d, double scale, double inv, int
     w1 = __float2int_rn(__fmul_rn(f, 2048.f));
 }
 
-template <bool OUT_U8>
-__global__ void __launch_bounds__(256)
-bpc_crop_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const int32_t* __restrict__ rois, int R,
-                const int32_t* __restrict__ n_rois_dev, int roi_first, int T, int nbands, uchar4 fill, int swap_rb,
-                const float* __restrict__ lut_g, float* __restrict__ outf, uint8_t* __restrict__ outb,
-                int32_t* __restrict__ status) {
-    extern __shared__ __align__(16) unsigned char raw[];
-    __shared__ RoiGeom g;
-    __shared__ YDesc yd[CROP_BAND];
-    __shared__ float lut[OUT_U8 ? 1 : 768];
-
-    const int tid = threadIdx.x, nth = blockDim.x;
-    const int roi = blockIdx.x / nbands, band = blockIdx.x - roi * nbands;
+// ------------------------------------------------------------------------------------------------------
+// prep: geometry + classification, one thread per ROI
+// ------------------------------------------------------------------------------------------------------
+__global__ void bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const int32_t* __restrict__ rois, int R,
+                                     const int32_t* __restrict__ n_rois_dev, int roi_first, int T,
+                                     RoiGeom* __restrict__ geom, int32_t* __restrict__ glist, int32_t* __restrict__ gcount,
+                                     int32_t* __restrict__ status) {
+    const int roi = blockIdx.x * blockDim.x + threadIdx.x;
     if (roi >= R) return;
-    if (n_rois_dev != nullptr && roi_first + roi >= *n_rois_dev) return;
-
-    if (tid == 0) {
-        const int32_t* r = rois + (size_t)roi * 5;
-        const int img = r[0], x1 = r[1], y1 = r[2], x2 = r[3], y2 = r[4];
-        const int w = x2 - x1, h = y2 - y1;
-        g.regime = 0;
-        g.w = w; g.h = h;
-        if (img >= 0 && img < B && x1 >= 0 && y1 >= 0 && x2 <= W && y2 <= H && w > 0 && h > 0 && w <= BPC_MAX_ROI_WIDTH) {
-            // letterbox geometry, data_utils.py:35-38,41-42 (Python round = half-to-even on the f64 product)
-            const double scale = ddiv((double)T, (double)max(h, w));
-            const int new_w = (int)__double2ll_rn(dmul((double)w, scale));
-            const int new_h = (int)__double2ll_rn(dmul((double)h, scale));
-            if (new_w >= 1 && new_h >= 1 && new_w <= T && new_h <= T) {
-                g.new_w = new_w; g.new_h = new_h;
-                g.dx = (T - new_w) / 2; g.dy = (T - new_h) / 2;
-                g.inv_x = ddiv((double)new_w, (double)w);
-                g.inv_y = ddiv((double)new_h, (double)h);
-                g.scale_x = ddiv(1.0, g.inv_x);
-                g.scale_y = ddiv(1.0, g.inv_y);
-                if (g.scale_x >= 1.0 && g.scale_y >= 1.0) {
-                    g.isx = __double2int_rn(g.scale_x);
-                    g.isy = __double2int_rn(g.scale_y);
-                    const bool fast = fabs(dsub(g.scale_x, (double)g.isx)) < 2.220446049250313e-16 &&
-                                      fabs(dsub(g.scale_y, (double)g.isy)) < 2.220446049250313e-16;
-                    g.regime = fast ? 2 : 1;
-                } else {
-                    g.regime = 3;
-                }
-                g.src = (unsigned long long)(uintptr_t)images + (((unsigned long long)img * H + y1) * W + x1) * 3ull;
-                g.pitch = ((3 * w + 15 + 15) / 16) * 16;
-                g.rows_fit = CROP_RAW_BYTES / g.pitch;
-            }
-        }
-        if (band == 0 && status != nullptr) status[roi] = (g.regime == 0) ? 1 : 0;
+    RoiGeom g;
+    g.scale_x = g.scale_y = g.inv_x = g.inv_y = 0.0;
+    g.src = 0ull;
+    g.new_w = g.new_h = g.dx = g.dy = 0;
+    g.regime = 0; g.cls = 0; g.isx = g.isy = 0; g.pitch = 16; g.pad_ = 0;
+    const int32_t* r = rois + (size_t)roi * 5;
+    const int img = r[0], x1 = r[1], y1 = r[2], x2 = r[3], y2 = r[4];
+    const int w = x2 - x1, h = y2 - y1;
+    g.w = w; g.h = h;
+    if (n_rois_dev != nullptr && roi_first + roi >= *n_rois_dev) {
+        g.cls = -1;
+        geom[roi] = g;
+        return;
     }
-    if (!OUT_U8)
-        for (int e = tid; e < 768; e += nth) lut[e] = lut_g[e];
-    __syncthreads();
+    if (img >= 0 && img < B && x1 >= 0 && y1 >= 0 && x2 <= W && y2 <= H && w > 0 && h > 0 && w <= BPC_MAX_ROI_WIDTH) {
+        // letterbox geometry, data_utils.py:35-38,41-42 (Python round = half-to-even on the f64 product)
+        const double scale = ddiv((double)T, (double)max(h, w));
+        const int new_w = (int)__double2ll_rn(dmul((double)w, scale));
+        const int new_h = (int)__double2ll_rn(dmul((double)h, scale));
+        if (new_w >= 1 && new_h >= 1 && new_w <= T && new_h <= T) {
+            g.new_w = new_w; g.new_h = new_h;
+            g.dx = (T - new_w) / 2; g.dy = (T - new_h) / 2;
+            g.inv_x = ddiv((double)new_w, (double)w);      // cv2.resize: inv_scale = dsize / ssize
+            g.inv_y = ddiv((double)new_h, (double)h);
+            g.scale_x = ddiv(1.0, g.inv_x);
+            g.scale_y = ddiv(1.0, g.inv_y);
+            if (g.scale_x >= 1.0 && g.scale_y >= 1.0) {
+                g.isx = __double2int_rn(g.scale_x);
+                g.isy = __double2int_rn(g.scale_y);
+                const bool fast = fabs(dsub(g.scale_x, (double)g.isx)) < 2.220446049250313e-16 &&
+                                  fabs(dsub(g.scale_y, (double)g.isy)) < 2.220446049250313e-16;
+                g.regime = fast ? 2 : 1;
+            } else {
+                g.regime = 3;
+            }
+            g.src = (unsigned long long)(uintptr_t)images + (((unsigned long long)img * H + y1) * W + x1) * 3ull;
+            g.pitch = ((3 * w + 15 + 16 + 15) / 16) * 16;   // misalignment + row + slack for zero-weight taps
+            const int rows_fit = FAST_BUF_BYTES / g.pitch;
+            if (g.regime == 1 && g.scale_x < 2.0 && g.scale_y < 2.0 && rows_fit >= 8) g.cls = 1;
+            else if (g.regime == 3 && rows_fit >= 8) g.cls = 3;
+            else g.cls = 2;
+        }
+    }
+    if (status != nullptr) status[roi] = (g.regime == 0) ? 1 : 0;
+    if (g.cls == 2) glist[atomicAdd(gcount, 1)] = roi;
+    geom[roi] = g;
+}
 
-    const int x = tid;                                  // output column
-    const int row0 = band * CROP_BAND, row1 = min(T, row0 + CROP_BAND);
-    const int regime = g.regime;
-    // per-plane padding values
-    const uint8_t fillc[3] = {fill.x, fill.y, fill.z};
+// ------------------------------------------------------------------------------------------------------
+// shared output helpers
+// ------------------------------------------------------------------------------------------------------
+template <bool OUT_U8>
+struct Out {
+    float* outf; uint8_t* outb;
+    const float* lut;           // shared memory [768]
+    int T, swap_rb;
+    uint8_t fillc[3];
     float padf[3];
-    if (!OUT_U8)
-        for (int p = 0; p < 3; ++p) padf[p] = lut[p * 256 + fillc[swap_rb ? 2 - p : p]];
 
-    auto store_px = [&](int y, int b0, int b1, int b2) {    // b* in source channel order
-        if (x >= T) return;
+    __device__ __forceinline__ void px(int roi, int y, int x, int b0, int b1, int b2) const {   // source channel order
         if (OUT_U8) {
             uint8_t* o = outb + (((size_t)roi * T + y) * T + x) * 3;
             o[0] = (uint8_t)b0; o[1] = (uint8_t)b1; o[2] = (uint8_t)b2;
@@ -161,9 +196,8 @@ bpc_crop_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const i
             o[(size_t)T * T] = lut[256 + b1];
             o[(size_t)2 * T * T] = lut[512 + s2];
         }
-    };
-    auto store_pad = [&](int y) {
-        if (x >= T) return;
+    }
+    __device__ __forceinline__ void pad(int roi, int y, int x) const {
         if (OUT_U8) {
             uint8_t* o = outb + (((size_t)roi * T + y) * T + x) * 3;
             o[0] = fillc[0]; o[1] = fillc[1]; o[2] = fillc[2];
@@ -171,21 +205,265 @@ bpc_crop_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const i
             float* o = outf + ((size_t)roi * 3 * T + y) * T + x;
             o[0] = padf[0]; o[(size_t)T * T] = padf[1]; o[(size_t)2 * T * T] = padf[2];
         }
-    };
-
-    if (regime == 0) {
-        for (int y = row0; y < row1; ++y) store_pad(y);
-        return;
     }
+    // rows [ra, rb) of all three planes = fill; collective over nth threads
+    __device__ void pad_rows(int roi, int ra, int rb, int tid, int nth) const {
+        if (rb <= ra) return;
+        if (OUT_U8) {
+            uint8_t* o = outb + ((size_t)roi * T + ra) * T * 3;
+            const int nbytes = (rb - ra) * T * 3;
+            for (int e = tid; e < nbytes; e += nth) o[e] = fillc[e % 3];
+        } else if ((T & 3) == 0) {
+            const int n4 = (rb - ra) * (T >> 2);
+            for (int p = 0; p < 3; ++p) {
+                float4* o = reinterpret_cast<float4*>(outf + ((size_t)(roi * 3 + p) * T + ra) * T);
+                const float4 v = make_float4(padf[p], padf[p], padf[p], padf[p]);
+                for (int e = tid; e < n4; e += nth) o[e] = v;
+            }
+        } else {
+            const int n1 = (rb - ra) * T;
+            for (int p = 0; p < 3; ++p) {
+                float* o = outf + ((size_t)(roi * 3 + p) * T + ra) * T;
+                for (int e = tid; e < n1; e += nth) o[e] = padf[p];
+            }
+        }
+    }
+};
+
+template <bool OUT_U8>
+__device__ __forceinline__ void out_init(Out<OUT_U8>& o, float* outf, uint8_t* outb, const float* lut_s, int T, int swap_rb, uchar4 fill) {
+    o.outf = outf; o.outb = outb; o.lut = lut_s; o.T = T; o.swap_rb = swap_rb;
+    o.fillc[0] = fill.x; o.fillc[1] = fill.y; o.fillc[2] = fill.z;
+    if (!OUT_U8)
+        for (int p = 0; p < 3; ++p) o.padf[p] = lut_s[p * 256 + o.fillc[swap_rb ? 2 - p : p]];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// fast kernel
+// ------------------------------------------------------------------------------------------------------
+// stage source rows [s_lo, s_lo + count) of the ROI into buf (16-byte cp.async of the aligned superset)
+__device__ __forceinline__ void fast_stage(unsigned char* buf, unsigned long long src0, unsigned long long rowstride,
+                                           unsigned long long img_end, int s_lo, int count, int pitch, int w, int tid) {
+    const int lane = tid & 31, wid = tid >> 5;
+    for (int r = wid; r < count; r += 8) {
+        const unsigned long long ga = src0 + (unsigned long long)(s_lo + r) * rowstride;
+        const unsigned long long al16 = ga & ~15ull;
+        const int need = (int)(ga - al16) + 3 * w + 8;             // + slack read by zero-weight taps
+        unsigned char* dst = buf + (size_t)r * pitch;
+        for (int v = lane; v * 16 < need; v += 32) {
+            const unsigned long long a = al16 + (unsigned long long)v * 16ull;
+            if (a + 16ull <= img_end) {
+                cp_async16(dst + v * 16, (const void*)(uintptr_t)a);
+            } else {                                               // last bytes of the image pool
+                unsigned int tmp[4] = {0u, 0u, 0u, 0u};
+                for (int b = 0; b < 16; ++b)
+                    if (a + b < img_end) tmp[b >> 2] |= (unsigned int)(*(const uint8_t*)(uintptr_t)(a + b)) << (8 * (b & 3));
+                *reinterpret_cast<uint4*>(dst + v * 16) = make_uint4(tmp[0], tmp[1], tmp[2], tmp[3]);
+            }
+        }
+    }
+    cp_async_commit();
+}
+
+__device__ __forceinline__ void h_area3(const uint8_t* __restrict__ p, float w0, float w1, float w2, float* h) {
+    float f[9];
+#pragma unroll
+    for (int e = 0; e < 9; ++e) f[e] = __uint2float_rn((unsigned int)p[e]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        h[c] = __fadd_rn(__fadd_rn(__fmul_rn(f[c], w0), __fmul_rn(f[3 + c], w1)), __fmul_rn(f[6 + c], w2));
+}
+
+__device__ __forceinline__ void h_lin(const uint8_t* __restrict__ p, int w0, int w1, int* h) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) h[c] = ((int)p[c] * w0 + (int)p[3 + c] * w1) >> 4;
+}
+
+template <bool OUT_U8>
+__global__ void __launch_bounds__(256, 3)
+bpc_crop_fast_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom, int R,
+                     int T, uchar4 fill, int swap_rb, const float* __restrict__ lut_g,
+                     float* __restrict__ outf, uint8_t* __restrict__ outb) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned char* buf0 = smem;
+    unsigned char* buf1 = smem + FAST_BUF_BYTES;
+    float4* ydw = reinterpret_cast<float4*>(smem + 2 * FAST_BUF_BYTES);          // [256] weights (+ n / b1 in .w)
+    int2* yds = reinterpret_cast<int2*>(smem + 2 * FAST_BUF_BYTES + 256 * 16);    // [256] rows
+    float* lut = reinterpret_cast<float*>(smem + 2 * FAST_BUF_BYTES + 256 * 24);  // [768]
+
+    const int tid = threadIdx.x;
+    const int roi = blockIdx.x;
+    const RoiGeom* gp = geom + roi;
+    const int cls = gp->cls;
+    if (cls == -1 || cls == 2) return;
+    if (!OUT_U8)
+        for (int e = tid; e < 768; e += 256) lut[e] = lut_g[e];
+    __syncthreads();
+    Out<OUT_U8> out;
+    out_init(out, outf, outb, lut, T, swap_rb, fill);
+    if (cls == 0) { out.pad_rows(roi, 0, T, tid, 256); return; }
+
+    const int w = gp->w, h = gp->h, new_w = gp->new_w, new_h = gp->new_h, dx0 = gp->dx, dy0 = gp->dy, pitch = gp->pitch;
+    const double scale_x = gp->scale_x, scale_y = gp->scale_y;
+    const unsigned long long src0 = gp->src;
+    const unsigned long long rowstride = (unsigned long long)W * 3ull;
+    const unsigned long long img_end = (unsigned long long)(uintptr_t)images + (unsigned long long)B * H * rowstride;
+    const int mis0 = (int)(src0 & 15ull), misstep = (int)(rowstride & 15ull);
+
+    out.pad_rows(roi, 0, dy0, tid, 256);
+    out.pad_rows(roi, dy0 + new_h, T, tid, 256);
+
+    const int x = tid, xr = x - dx0;
+    const bool incol = x < T;
+    const bool active = incol && xr >= 0 && xr < new_w;
+    const int rows_fit = FAST_BUF_BYTES / pitch;
+
+    if (cls == 1) {
+        // ---------------- regime 1, at most 3 taps per axis ----------------
+        int xs = 0, xn = 0;
+        float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+        if (active) area_taps3(xr, scale_x, w, xs, xn, w0, w1, w2);
+        if (tid < new_h) {
+            int ys, yn; float b0, b1, b2;
+            area_taps3(tid, scale_y, h, ys, yn, b0, b1, b2);
+            ydw[tid] = make_float4(b0, b1, b2, __int_as_float(yn));
+            yds[tid] = make_int2(ys, ys + yn - 1);
+        }
+        __syncthreads();
+        const int band_h = max(1, min(FAST_MAX_BAND, (int)((double)(rows_fit - 3) / scale_y)));
+        const int nb = (new_h + band_h - 1) / band_h;
+        const int xo = 3 * xs;
+        int crow = -1;
+        float hc[3] = {0.f, 0.f, 0.f};
+        // prologue: stage band 0
+        {
+            const int y1 = min(new_h, band_h);
+            const int s_lo = yds[0].x, s_hi = yds[y1 - 1].y;
+            fast_stage(buf0, src0, rowstride, img_end, s_lo, s_hi - s_lo + 1, pitch, w, tid);
+        }
+        for (int b = 0; b < nb; ++b) {
+            unsigned char* cur = (b & 1) ? buf1 : buf0;
+            cp_async_wait_all();
+            __syncthreads();
+            if (b + 1 < nb) {
+                const int y0n = (b + 1) * band_h, y1n = min(new_h, y0n + band_h);
+                const int s_lo = yds[y0n].x, s_hi = yds[y1n - 1].y;
+                fast_stage((b & 1) ? buf0 : buf1, src0, rowstride, img_end, s_lo, s_hi - s_lo + 1, pitch, w, tid);
+            }
+            const int y0 = b * band_h, y1 = min(new_h, y0 + band_h);
+            const int s_lo = yds[y0].x;
+            if (active) {
+                for (int yr = y0; yr < y1; ++yr) {
+                    const float4 d = ydw[yr];
+                    const int ys = yds[yr].x;
+                    const int n = __float_as_int(d.w);
+                    const int r0 = ys - s_lo;
+                    const uint8_t* p = cur + (size_t)r0 * pitch + ((mis0 + (ys * misstep)) & 15) + xo;
+                    if (ys != crow) h_area3(p, w0, w1, w2, hc);
+                    float acc[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) acc[c] = __fmul_rn(d.x, hc[c]);
+                    if (n > 1) {
+                        const uint8_t* p1 = cur + (size_t)(r0 + 1) * pitch + ((mis0 + ((ys + 1) * misstep)) & 15) + xo;
+                        h_area3(p1, w0, w1, w2, hc);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(d.y, hc[c]));
+                    }
+                    if (n > 2) {
+                        const uint8_t* p2 = cur + (size_t)(r0 + 2) * pitch + ((mis0 + ((ys + 2) * misstep)) & 15) + xo;
+                        h_area3(p2, w0, w1, w2, hc);
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(d.z, hc[c]));
+                    }
+                    crow = ys + n - 1;
+                    out.px(roi, dy0 + yr, x, min(255, __float2int_rn(acc[0])), min(255, __float2int_rn(acc[1])),
+                           min(255, __float2int_rn(acc[2])));
+                }
+            } else if (incol) {
+                for (int yr = y0; yr < y1; ++yr) out.pad(roi, dy0 + yr, x);
+            }
+        }
+    } else {
+        // ---------------- regime 3: fixed-point bilinear ----------------
+        int xs = 0, xw0 = 0, xw1 = 0, xedge = 0;
+        if (active) {
+            linear_coef(xr, scale_x, gp->inv_x, w, xs, xw0, xw1, xedge);
+            if (xedge) { xw0 = 2048; xw1 = 0; }                    // D = S[sx] * ONE beyond xmax
+        }
+        if (tid < new_h) {
+            int s0, b0, b1, edge;
+            linear_coef(tid, scale_y, gp->inv_y, h, s0, b0, b1, edge);
+            const int s1 = min(s0 + 1, h - 1);
+            ydw[tid] = make_float4(__int_as_float(b0), __int_as_float(b1), 0.f, 0.f);
+            yds[tid] = make_int2(s0, s1);
+        }
+        __syncthreads();
+        const double sy_eff = scale_y < 1.0 ? 1.0 : scale_y;
+        const int band_h = max(1, min(FAST_MAX_BAND, (int)((double)(rows_fit - 3) / sy_eff)));
+        const int nb = (new_h + band_h - 1) / band_h;
+        const int xo = 3 * xs;
+        int rowA = -1, rowB = -1;
+        int HA[3] = {0, 0, 0}, HB[3] = {0, 0, 0};
+        {
+            const int y1 = min(new_h, band_h);
+            const int s_lo = yds[0].x, s_hi = yds[y1 - 1].y;
+            fast_stage(buf0, src0, rowstride, img_end, s_lo, s_hi - s_lo + 1, pitch, w, tid);
+        }
+        for (int b = 0; b < nb; ++b) {
+            unsigned char* cur = (b & 1) ? buf1 : buf0;
+            cp_async_wait_all();
+            __syncthreads();
+            if (b + 1 < nb) {
+                const int y0n = (b + 1) * band_h, y1n = min(new_h, y0n + band_h);
+                const int s_lo = yds[y0n].x, s_hi = yds[y1n - 1].y;
+                fast_stage((b & 1) ? buf0 : buf1, src0, rowstride, img_end, s_lo, s_hi - s_lo + 1, pitch, w, tid);
+            }
+            const int y0 = b * band_h, y1 = min(new_h, y0 + band_h);
+            const int s_lo = yds[y0].x;
+            if (active) {
+                for (int yr = y0; yr < y1; ++yr) {
+                    const float4 d = ydw[yr];
+                    const int2 rr = yds[yr];
+                    const int b0 = __float_as_int(d.x), b1 = __float_as_int(d.y);
+                    if (rr.x != rowA) {
+                        if (rr.x == rowB) { HA[0] = HB[0]; HA[1] = HB[1]; HA[2] = HB[2]; }
+                        else h_lin(cur + (size_t)(rr.x - s_lo) * pitch + ((mis0 + (rr.x * misstep)) & 15) + xo, xw0, xw1, HA);
+                        rowA = rr.x;
+                    }
+                    if (rr.y != rowB) {
+                        if (rr.y == rowA) { HB[0] = HA[0]; HB[1] = HA[1]; HB[2] = HA[2]; }
+                        else h_lin(cur + (size_t)(rr.y - s_lo) * pitch + ((mis0 + (rr.y * misstep)) & 15) + xo, xw0, xw1, HB);
+                        rowB = rr.y;
+                    }
+                    int o[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) o[c] = ((((b0 * HA[c]) >> 16) + ((b1 * HB[c]) >> 16) + 2) >> 2) & 255;
+                    out.px(roi, dy0 + yr, x, o[0], o[1], o[2]);
+                }
+            } else if (incol) {
+                for (int yr = y0; yr < y1; ++yr) out.pad(roi, dy0 + yr, x);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// generic kernel: any regime / scale, persistent CTAs over (ROI, band) items of the generic list
+// ------------------------------------------------------------------------------------------------------
+template <bool OUT_U8>
+__device__ void crop_generic_band(unsigned char* raw, YDesc* yd, const Out<OUT_U8>& out, const RoiGeom& g, int roi, int band,
+                                  const uint8_t* __restrict__ images, int B, int H, int W, int T, int tid, int nth) {
+    const int x = tid;
+    const bool incol = x < T;
+    const int row0 = band * CROP_BAND, row1 = min(T, row0 + CROP_BAND);
+    const int regime = g.regime;
     const int dy0 = g.dy, new_h = g.new_h, new_w = g.new_w, dx0 = g.dx;
-    // rows of the band inside the resized image: [ya, yb) in resized coordinates
     const int ya = max(row0, dy0) - dy0, yb = min(row1, dy0 + new_h) - dy0;
-    for (int y = row0; y < row1; ++y)
-        if (y < dy0 || y >= dy0 + new_h) store_pad(y);
-    if (ya >= yb) return;
+    out.pad_rows(roi, row0, min(row1, dy0), tid, nth);
+    out.pad_rows(roi, max(row0, dy0 + new_h), row1, tid, nth);
+    if (ya >= yb) return;                                            // uniform
 
     const int w = g.w, h = g.h;
-    // ---- per-row descriptors ----------------------------------------------------------------------------
     if (tid < yb - ya) {
         YDesc d;
         const int yr = ya + tid;
@@ -201,9 +479,8 @@ bpc_crop_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const i
         }
         yd[tid] = d;
     }
-    // ---- per-thread column descriptor -------------------------------------------------------------------
     const int xr = x - dx0;
-    const bool active = (x < T) && xr >= 0 && xr < new_w;
+    const bool active = incol && xr >= 0 && xr < new_w;
     int xs = 0, xn = 0, xflags = 0, xw0 = 0, xw1 = 0, xedge = 0;
     float af = 0.f, am = 0.f, al = 0.f;
     if (active) {
@@ -215,18 +492,18 @@ bpc_crop_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const i
 
     const int s_lo = yd[0].start;
     const int s_hi = (regime == 3) ? yd[yb - ya - 1].n : (yd[yb - ya - 1].start + yd[yb - ya - 1].n - 1);
-    const int pitch = g.pitch, rows_fit = g.rows_fit;
+    const int pitch = ((3 * w + 15 + 15) / 16) * 16;
+    const int rows_fit = CROP_RAW_BYTES / pitch;
     const unsigned long long src0 = g.src;
     const unsigned long long rowstride = (unsigned long long)W * 3ull;
     const unsigned long long img_end = (unsigned long long)(uintptr_t)images + (unsigned long long)B * H * rowstride;
     const int nvec = pitch >> 4;
     const int lane = tid & 31, wid = tid >> 5, nwarps = nth >> 5;
 
-    // streaming state (uniform across the CTA except for x)
-    int yr = ya, t = 0;
+    int yr = ya, t = 0;                      // streaming state, uniform across the CTA except for x
     float acc[3] = {0.f, 0.f, 0.f};
     int iacc[3] = {0, 0, 0};
-    int cacheA = -1, cacheB = -1;          // source rows held in hA / hB
+    int cacheA = -1, cacheB = -1;
     float hA[3] = {0.f, 0.f, 0.f};
     int HA[3] = {0, 0, 0}, HB[3] = {0, 0, 0};
 
@@ -237,14 +514,14 @@ bpc_crop_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const i
         for (int r = wid; r < rows; r += nwarps) {
             const unsigned long long ga = src0 + (unsigned long long)(chunk + r) * rowstride;
             const unsigned long long al16 = ga & ~15ull;
-            const int need = (int)(ga - al16) + 3 * w;                 // bytes from the aligned start
+            const int need = (int)(ga - al16) + 3 * w;
             for (int v = lane; v < nvec; v += 32) {
                 if (v * 16 >= need) break;
                 const unsigned long long a = al16 + (unsigned long long)v * 16ull;
                 uint4 q;
                 if (a + 16ull <= img_end) {
                     q = ld_nc_v4((const void*)(uintptr_t)a);
-                } else {                                                // last bytes of the image pool
+                } else {
                     unsigned int tmp[4] = {0u, 0u, 0u, 0u};
                     for (int b = 0; b < 16; ++b)
                         if (a + b < img_end) tmp[b >> 2] |= (unsigned int)(*(const uint8_t*)(uintptr_t)(a + b)) << (8 * (b & 3));
@@ -286,9 +563,9 @@ bpc_crop_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const i
                     int o[3];
                     for (int c = 0; c < 3; ++c)
                         o[c] = ((((b0 * (HA[c] >> 4)) >> 16) + ((b1 * (HB[c] >> 4)) >> 16) + 2) >> 2) & 255;
-                    store_px(dy0 + yr, o[0], o[1], o[2]);
-                } else {
-                    store_pad(dy0 + yr);
+                    out.px(roi, dy0 + yr, x, o[0], o[1], o[2]);
+                } else if (incol) {
+                    out.pad(roi, dy0 + yr, x);
                 }
                 ++yr;
             }
@@ -336,15 +613,41 @@ bpc_crop_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const i
                             const float sc = __fdiv_rn(1.f, (float)(g.isx * g.isy));
                             for (int c = 0; c < 3; ++c) o[c] = min(255, max(0, __float2int_rn(__fmul_rn(__int2float_rn(iacc[c]), sc))));
                         }
-                        store_px(dy0 + yr, o[0], o[1], o[2]);
-                    } else {
-                        store_pad(dy0 + yr);
+                        out.px(roi, dy0 + yr, x, o[0], o[1], o[2]);
+                    } else if (incol) {
+                        out.pad(roi, dy0 + yr, x);
                     }
                     ++yr; t = 0;
                 }
             }
             if (yr < yb) chunk = yd[yr - ya].start + t;
         }
+    }
+}
+
+template <bool OUT_U8>
+__global__ void __launch_bounds__(256)
+bpc_crop_generic_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom,
+                        const int32_t* __restrict__ glist, const int32_t* __restrict__ gcount, int T, int nbands,
+                        uchar4 fill, int swap_rb, const float* __restrict__ lut_g, float* __restrict__ outf, uint8_t* __restrict__ outb) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    __shared__ RoiGeom g;
+    __shared__ YDesc yd[CROP_BAND];
+    __shared__ float lut[OUT_U8 ? 1 : 768];
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const long long items = (long long)(*gcount) * nbands;
+    if (blockIdx.x >= items) return;
+    if (!OUT_U8)
+        for (int e = tid; e < 768; e += nth) lut[e] = lut_g[e];
+    __syncthreads();
+    Out<OUT_U8> out;
+    out_init(out, outf, outb, lut, T, swap_rb, fill);
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const int roi = glist[item / nbands], band = (int)(item % nbands);
+        __syncthreads();
+        if (tid == 0) g = geom[roi];
+        __syncthreads();
+        crop_generic_band<OUT_U8>(raw, yd, out, g, roi, band, images, B, H, W, T, tid, nth);
     }
 }
 
@@ -358,25 +661,45 @@ __global__ void bpc_lut_kernel(float m0, float m1, float m2, float s0, float s1,
     lut[t] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), mean), sd);
 }
 
+static size_t crop_workspace_bytes(int R) {
+    return (size_t)R * sizeof(RoiGeom) + ((size_t)R + 4) * sizeof(int32_t) + 64;
+}
+
+constexpr int FAST_SMEM = 2 * FAST_BUF_BYTES + 256 * 24 + 768 * 4;
+
 template <bool OUT_U8>
 static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R, const int32_t* n_rois_dev,
                        int roi_first, int T, const uint8_t* fill, int swap_rb, const float* lut, float* outf, uint8_t* outb,
-                       int32_t* status, void* stream) {
+                       int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
     if (R < 0 || B < 1 || H < 1 || W < 1 || T < 1 || T > 256 || !fill) return BPC_EINVAL;
-    if (R > 0 && (!images || !rois || (!OUT_U8 && (!lut || !outf)) || (OUT_U8 && !outb))) return BPC_EINVAL;
-    if (((uintptr_t)images & 15) != 0) return BPC_EALIGN;
+    if (R > 0 && (!images || !rois || !workspace || (!OUT_U8 && (!lut || !outf)) || (OUT_U8 && !outb))) return BPC_EINVAL;
+    if (((uintptr_t)images & 15) != 0 || ((uintptr_t)workspace & 15) != 0) return BPC_EALIGN;
     if (R == 0) return BPC_OK;
-    const int nbands = (T + CROP_BAND - 1) / CROP_BAND;
-    if ((long long)R * nbands > 0x7fffffffLL) return BPC_ETOOBIG;
-    const int threads = ((T + 31) / 32) * 32;
+    if (workspace_bytes < crop_workspace_bytes(R)) return BPC_EWORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    RoiGeom* geom = (RoiGeom*)workspace;
+    int32_t* gcount = (int32_t*)((unsigned char*)workspace + (size_t)R * sizeof(RoiGeom));
+    int32_t* glist = gcount + 4;
     static bool attr_set[2] = {false, false};
     if (!attr_set[OUT_U8]) {
-        cudaError_t e = cudaFuncSetAttribute(bpc_crop_kernel<OUT_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROP_RAW_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(bpc_crop_generic_kernel<OUT_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROP_RAW_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaFuncSetAttribute(bpc_crop_fast_kernel<OUT_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM);
         if (e != cudaSuccess) return (int)e;
         attr_set[OUT_U8] = true;
     }
-    bpc_crop_kernel<OUT_U8><<<R * nbands, threads, CROP_RAW_BYTES, (cudaStream_t)stream>>>(
-        images, B, H, W, rois, R, n_rois_dev, roi_first, T, nbands, make_uchar4(fill[0], fill[1], fill[2], 0), swap_rb, lut, outf, outb, status);
+    cudaError_t e = cudaMemsetAsync(gcount, 0, 16, st);
+    if (e != cudaSuccess) return (int)e;
+    bpc_crop_prep_kernel<<<(R + 127) / 128, 128, 0, st>>>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, geom, glist, gcount, status);
+    BPC_LAUNCH_CHECK();
+    const uchar4 f4 = make_uchar4(fill[0], fill[1], fill[2], 0);
+    bpc_crop_fast_kernel<OUT_U8><<<R, 256, FAST_SMEM, st>>>(images, B, H, W, geom, R, T, f4, swap_rb, lut, outf, outb);
+    BPC_LAUNCH_CHECK();
+    const int nbands = (T + CROP_BAND - 1) / CROP_BAND;
+    const long long max_items = (long long)R * nbands;
+    const int grid = (int)(max_items < 148 * 4 ? max_items : 148 * 4);
+    const int threads = ((T + 31) / 32) * 32;
+    bpc_crop_generic_kernel<OUT_U8><<<grid, threads, CROP_RAW_BYTES, st>>>(images, B, H, W, geom, glist, gcount, T, nbands, f4, swap_rb, lut, outf, outb);
     BPC_LAUNCH_CHECK();
     return BPC_OK;
 }
@@ -385,17 +708,22 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
 
 using namespace bpc;
 
+extern "C" size_t bpc_roi_crop_workspace_bytes(int R) { return R < 0 ? 0 : crop_workspace_bytes(R); }
+
 extern "C" int bpc_roi_crop(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R,
                             const int32_t* n_rois_dev, int roi_first, int T, const uint8_t* fill, int swap_rb,
-                            const float* lut, float* out, int32_t* status, void* stream) {
+                            const float* lut, float* out, int32_t* status, void* workspace, size_t workspace_bytes,
+                            void* stream) {
     if (((uintptr_t)out & 15) != 0) return BPC_EALIGN;
-    return launch_crop<false>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, fill, swap_rb, lut, out, nullptr, status, stream);
+    return launch_crop<false>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, fill, swap_rb, lut, out, nullptr, status,
+                              workspace, workspace_bytes, stream);
 }
 
 extern "C" int bpc_roi_crop_u8(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R,
                                const int32_t* n_rois_dev, int roi_first, int T, const uint8_t* fill, uint8_t* out,
-                               int32_t* status, void* stream) {
-    return launch_crop<true>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, fill, 0, nullptr, nullptr, out, status, stream);
+                               int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+    return launch_crop<true>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, fill, 0, nullptr, nullptr, out, status,
+                             workspace, workspace_bytes, stream);
 }
 
 extern "C" int bpc_normalise_lut(const float* mean, const float* std_, float* lut, void* stream) {

@@ -148,15 +148,20 @@ int bpc_build_rois(const int32_t* boxes, const int32_t* idx, const int32_t* n, c
  *   out      float [R][3][T][T]   (16-byte aligned)
  *   status   optional int32 [R]: 0 ok, 1 = ROI rejected (empty box, resized side < 1, out of
  *            image, wider than BPC_MAX_ROI_WIDTH); a rejected ROI's output is all fill colour
+ *   workspace   bpc_roi_crop_workspace_bytes(R) bytes of device scratch (16-byte aligned): per-ROI
+ *               geometry records and the list of ROIs taking the generic path
  * bpc_roi_crop_u8 writes the uint8 letterboxed image itself, uint8 [R][T][T][3] in source channel
  * order -- exactly what letterbox_preserving_aspect_ratio returns.
  */
+size_t bpc_roi_crop_workspace_bytes(int R);
 int bpc_roi_crop(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R,
                  const int32_t* n_rois_dev, int roi_first, int T, const uint8_t* fill, int swap_rb,
-                 const float* lut, float* out, int32_t* status, void* stream);
+                 const float* lut, float* out, int32_t* status,
+                 void* workspace, size_t workspace_bytes, void* stream);
 int bpc_roi_crop_u8(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R,
                     const int32_t* n_rois_dev, int roi_first, int T, const uint8_t* fill,
-                    uint8_t* out, int32_t* status, void* stream);
+                    uint8_t* out, int32_t* status,
+                    void* workspace, size_t workspace_bytes, void* stream);
 /* lut[c][v] = (v/255 - mean[c]) / std[c] in float32 with true divisions, as torchvision's
  * to_tensor (.div(255)) + normalize (.sub_(mean).div_(std)); process_pose.py:207-209. */
 int bpc_normalise_lut(const float* mean_host3, const float* std_host3, float* lut, void* stream);
