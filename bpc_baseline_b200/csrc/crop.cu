@@ -265,13 +265,55 @@ __device__ __forceinline__ void fast_stage(unsigned char* buf, unsigned long lon
     cp_async_commit();
 }
 
-__device__ __forceinline__ void h_area3(const uint8_t* __restrict__ p, float w0, float w1, float w2, float* h) {
-    float f[9];
+// ---- packed float32x2 arithmetic (sm_100a FFMA2 / FADD2 / FMUL2), every lane IEEE round-to-nearest ----
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// ptxas 12.9 contracts a mul.rn.f32x2 feeding an add.rn.f32x2 into one FFMA2 (even with --fmad=false and
+// volatile asm; the scalar forms are left alone): one rounding where OpenCV rounds twice, seen as 1-LSB
+// errors in ~1e-4 of the pixels.  fma(a, b, -0.0) with a literal -0 is simplified back to a multiply and
+// contracted again.  The vertical pass therefore forms its rounded products as fma(a, b, z) with
+// z = (-0.0f, -0.0f) held in a register whose value the compiler cannot prove: the same value as a * b for
+// non-negative operands, and an FFMA2 cannot be merged with the add that follows.
+__device__ __forceinline__ u64 fprod2(u64 a, u64 b, u64 negzero2) { return ffma2(a, b, negzero2); }
+
+// float(2^23 + byte k of v): the byte dropped into the mantissa of 8388608.0f (one PRMT, no I2F)
+template <int K>
+__device__ __forceinline__ float magic_byte(unsigned v) { return __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540 + K)); }
+
+// Column weights of the 3-slot horizontal pass.  fl(b * w) is computed as fma(2^23 + b, w, -(2^23 * w)):
+// the product 2^23 * w is exact, so the fused result is the correctly rounded b * w, bit-identical to
+// OpenCV's separately rounded multiply.
+struct ColW {
+    u64 w01[3], c01[3];     // (w, w) and (-2^23 w, -2^23 w) per slot, channels 0 and 1
+    float w2[3], c2[3];     // channel 2
+    __device__ __forceinline__ void set(float a, float b, float c) {
+        const float w[3] = {a, b, c};
 #pragma unroll
-    for (int e = 0; e < 9; ++e) f[e] = __uint2float_rn((unsigned int)p[e]);
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-        h[c] = __fadd_rn(__fadd_rn(__fmul_rn(f[c], w0), __fmul_rn(f[3 + c], w1)), __fmul_rn(f[6 + c], w2));
+        for (int k = 0; k < 3; ++k) {
+            const float cc = __fmul_rn(w[k], -8388608.0f);
+            w01[k] = pack2(w[k], w[k]); c01[k] = pack2(cc, cc); w2[k] = w[k]; c2[k] = cc;
+        }
+    }
+};
+
+// horizontal pass of one source row for one output column: 9 bytes starting at byte offset (a4 + sh/8)
+__device__ __forceinline__ void h_area3(const unsigned char* __restrict__ base, int a4, int sh, const ColW& cw, u64& h01, float& h2) {
+    const unsigned q0 = *reinterpret_cast<const unsigned*>(base + a4);
+    const unsigned q1 = *reinterpret_cast<const unsigned*>(base + a4 + 4);
+    const unsigned q2 = *reinterpret_cast<const unsigned*>(base + a4 + 8);
+    const unsigned v0 = __funnelshift_r(q0, q1, sh), v1 = __funnelshift_r(q1, q2, sh), v2 = q2 >> sh;
+    // pixel k = bytes 3k .. 3k+2
+    const u64 p0 = ffma2(pack2(magic_byte<0>(v0), magic_byte<1>(v0)), cw.w01[0], cw.c01[0]);
+    const u64 p1 = ffma2(pack2(magic_byte<3>(v0), magic_byte<0>(v1)), cw.w01[1], cw.c01[1]);
+    const u64 p2 = ffma2(pack2(magic_byte<2>(v1), magic_byte<3>(v1)), cw.w01[2], cw.c01[2]);
+    const float r0 = __fmaf_rn(magic_byte<2>(v0), cw.w2[0], cw.c2[0]);
+    const float r1 = __fmaf_rn(magic_byte<1>(v1), cw.w2[1], cw.c2[1]);
+    const float r2 = __fmaf_rn(magic_byte<0>(v2), cw.w2[2], cw.c2[2]);
+    h01 = fadd2(fadd2(p0, p1), p2);
+    h2 = __fadd_rn(__fadd_rn(r0, r1), r2);
 }
 
 __device__ __forceinline__ void h_lin(const uint8_t* __restrict__ p, int w0, int w1, int* h) {
@@ -279,18 +321,23 @@ __device__ __forceinline__ void h_lin(const uint8_t* __restrict__ p, int w0, int
     for (int c = 0; c < 3; ++c) h[c] = ((int)p[c] * w0 + (int)p[3 + c] * w1) >> 4;
 }
 
-template <bool OUT_U8>
+// cvRound(v) for 0 <= v < 2^22 without F2I: adding 2^23 leaves round-half-even(v) in the low mantissa bits
+__device__ __forceinline__ int round_u8(float v) { return min(255, __float_as_int(__fadd_rn(v, 8388608.0f)) & 0x1ff); }
+
+// TT = compile-time target size (0: run-time T); ALIGNED = the image row pitch W*3 is a multiple of 16 bytes
+template <bool OUT_U8, int TT, bool ALIGNED>
 __global__ void __launch_bounds__(256, 3)
 bpc_crop_fast_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom, int R,
-                     int T, uchar4 fill, int swap_rb, const float* __restrict__ lut_g,
+                     int Trt, uchar4 fill, int swap_rb, const float* __restrict__ lut_g,
                      float* __restrict__ outf, uint8_t* __restrict__ outb) {
     extern __shared__ __align__(16) unsigned char smem[];
     unsigned char* buf0 = smem;
     unsigned char* buf1 = smem + FAST_BUF_BYTES;
-    float4* ydw = reinterpret_cast<float4*>(smem + 2 * FAST_BUF_BYTES);          // [256] weights (+ n / b1 in .w)
-    int2* yds = reinterpret_cast<int2*>(smem + 2 * FAST_BUF_BYTES + 256 * 16);    // [256] rows
+    float4* ydw = reinterpret_cast<float4*>(smem + 2 * FAST_BUF_BYTES);          // [256] weights (+ n in .w)
+    int2* yds = reinterpret_cast<int2*>(smem + 2 * FAST_BUF_BYTES + 256 * 16);    // [256] first / last source row
     float* lut = reinterpret_cast<float*>(smem + 2 * FAST_BUF_BYTES + 256 * 24);  // [768]
 
+    const int T = TT ? TT : Trt;
     const int tid = threadIdx.x;
     const int roi = blockIdx.x;
     const RoiGeom* gp = geom + roi;
@@ -308,21 +355,35 @@ bpc_crop_fast_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
     const unsigned long long src0 = gp->src;
     const unsigned long long rowstride = (unsigned long long)W * 3ull;
     const unsigned long long img_end = (unsigned long long)(uintptr_t)images + (unsigned long long)B * H * rowstride;
-    const int mis0 = (int)(src0 & 15ull), misstep = (int)(rowstride & 15ull);
+    const int mis0 = (int)(src0 & 15ull), misstep = ALIGNED ? 0 : (int)(rowstride & 15ull);
 
+    // letterbox padding: whole rows above / below, column strips left / right of the resized image
     out.pad_rows(roi, 0, dy0, tid, 256);
     out.pad_rows(roi, dy0 + new_h, T, tid, 256);
+    {
+        const int npc = T - new_w;
+        if (npc > 0)
+            for (int r = tid >> 5; r < new_h; r += 8)
+                for (int c = tid & 31; c < npc; c += 32) out.pad(roi, dy0 + r, c < dx0 ? c : c + new_w);
+    }
 
     const int x = tid, xr = x - dx0;
-    const bool incol = x < T;
-    const bool active = incol && xr >= 0 && xr < new_w;
+    const bool active = x < T && xr >= 0 && xr < new_w;
     const int rows_fit = FAST_BUF_BYTES / pitch;
+    const bool swap = swap_rb != 0;
+    // per-thread output pointer of (plane 0, row dy0, column x); advanced by T per output row
+    float* orow = outf + ((size_t)roi * 3 * T + dy0) * T + x;
+    const size_t plane = (size_t)T * T;
 
     if (cls == 1) {
         // ---------------- regime 1, at most 3 taps per axis ----------------
         int xs = 0, xn = 0;
-        float w0 = 0.f, w1 = 0.f, w2 = 0.f;
-        if (active) area_taps3(xr, scale_x, w, xs, xn, w0, w1, w2);
+        ColW cw;
+        {
+            float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+            if (active) area_taps3(xr, scale_x, w, xs, xn, w0, w1, w2);
+            cw.set(w0, w1, w2);
+        }
         if (tid < new_h) {
             int ys, yn; float b0, b1, b2;
             area_taps3(tid, scale_y, h, ys, yn, b0, b1, b2);
@@ -332,17 +393,19 @@ bpc_crop_fast_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
         __syncthreads();
         const int band_h = max(1, min(FAST_MAX_BAND, (int)((double)(rows_fit - 3) / scale_y)));
         const int nb = (new_h + band_h - 1) / band_h;
-        const int xo = 3 * xs;
+        const int colc = 3 * xs + (ALIGNED ? mis0 : 0);          // byte offset of the column inside a staged row
         int crow = -1;
-        float hc[3] = {0.f, 0.f, 0.f};
-        // prologue: stage band 0
+        const float nz = __int_as_float((int)(0x80000000u | (unsigned)fill.w));     // -0.0f: fill.w is 0 at run time
+        const u64 nz2 = pack2(nz, nz);
+        u64 hc01 = 0ull;
+        float hc2 = 0.f;
         {
             const int y1 = min(new_h, band_h);
             const int s_lo = yds[0].x, s_hi = yds[y1 - 1].y;
             fast_stage(buf0, src0, rowstride, img_end, s_lo, s_hi - s_lo + 1, pitch, w, tid);
         }
         for (int b = 0; b < nb; ++b) {
-            unsigned char* cur = (b & 1) ? buf1 : buf0;
+            const unsigned char* cur = (b & 1) ? buf1 : buf0;
             cp_async_wait_all();
             __syncthreads();
             if (b + 1 < nb) {
@@ -357,30 +420,38 @@ bpc_crop_fast_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                     const float4 d = ydw[yr];
                     const int ys = yds[yr].x;
                     const int n = __float_as_int(d.w);
-                    const int r0 = ys - s_lo;
-                    const uint8_t* p = cur + (size_t)r0 * pitch + ((mis0 + (ys * misstep)) & 15) + xo;
-                    if (ys != crow) h_area3(p, w0, w1, w2, hc);
-                    float acc[3];
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) acc[c] = __fmul_rn(d.x, hc[c]);
+                    int a = (ys - s_lo) * pitch + colc;
+                    if (!ALIGNED) a += (mis0 + ys * misstep) & 15;
+                    if (ys != crow) h_area3(cur, a & ~3, (a & 3) * 8, cw, hc01, hc2);
+                    u64 acc01 = fprod2(pack2(d.x, d.x), hc01, nz2);
+                    float acc2 = __fmul_rn(d.x, hc2);
                     if (n > 1) {
-                        const uint8_t* p1 = cur + (size_t)(r0 + 1) * pitch + ((mis0 + ((ys + 1) * misstep)) & 15) + xo;
-                        h_area3(p1, w0, w1, w2, hc);
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(d.y, hc[c]));
+                        int a1 = a + pitch;
+                        if (!ALIGNED) a1 = (ys + 1 - s_lo) * pitch + colc + ((mis0 + (ys + 1) * misstep) & 15);
+                        h_area3(cur, a1 & ~3, (a1 & 3) * 8, cw, hc01, hc2);
+                        acc01 = fadd2(acc01, fprod2(pack2(d.y, d.y), hc01, nz2));
+                        acc2 = __fadd_rn(acc2, __fmul_rn(d.y, hc2));
                     }
                     if (n > 2) {
-                        const uint8_t* p2 = cur + (size_t)(r0 + 2) * pitch + ((mis0 + ((ys + 2) * misstep)) & 15) + xo;
-                        h_area3(p2, w0, w1, w2, hc);
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) acc[c] = __fadd_rn(acc[c], __fmul_rn(d.z, hc[c]));
+                        int a2 = a + 2 * pitch;
+                        if (!ALIGNED) a2 = (ys + 2 - s_lo) * pitch + colc + ((mis0 + (ys + 2) * misstep) & 15);
+                        h_area3(cur, a2 & ~3, (a2 & 3) * 8, cw, hc01, hc2);
+                        acc01 = fadd2(acc01, fprod2(pack2(d.z, d.z), hc01, nz2));
+                        acc2 = __fadd_rn(acc2, __fmul_rn(d.z, hc2));
                     }
                     crow = ys + n - 1;
-                    out.px(roi, dy0 + yr, x, min(255, __float2int_rn(acc[0])), min(255, __float2int_rn(acc[1])),
-                           min(255, __float2int_rn(acc[2])));
+                    float a0f, a1f;
+                    unpack2(acc01, a0f, a1f);
+                    const int o0 = round_u8(a0f), o1 = round_u8(a1f), o2 = round_u8(acc2);
+                    if (OUT_U8) {
+                        out.px(roi, dy0 + yr, x, o0, o1, o2);
+                    } else {
+                        float* o = orow + (size_t)yr * T;
+                        o[0] = lut[swap ? o2 : o0];
+                        o[plane] = lut[256 + o1];
+                        o[2 * plane] = lut[512 + (swap ? o0 : o2)];
+                    }
                 }
-            } else if (incol) {
-                for (int yr = y0; yr < y1; ++yr) out.pad(roi, dy0 + yr, x);
             }
         }
     } else {
@@ -410,7 +481,7 @@ bpc_crop_fast_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             fast_stage(buf0, src0, rowstride, img_end, s_lo, s_hi - s_lo + 1, pitch, w, tid);
         }
         for (int b = 0; b < nb; ++b) {
-            unsigned char* cur = (b & 1) ? buf1 : buf0;
+            const unsigned char* cur = (b & 1) ? buf1 : buf0;
             cp_async_wait_all();
             __syncthreads();
             if (b + 1 < nb) {
@@ -427,21 +498,26 @@ bpc_crop_fast_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                     const int b0 = __float_as_int(d.x), b1 = __float_as_int(d.y);
                     if (rr.x != rowA) {
                         if (rr.x == rowB) { HA[0] = HB[0]; HA[1] = HB[1]; HA[2] = HB[2]; }
-                        else h_lin(cur + (size_t)(rr.x - s_lo) * pitch + ((mis0 + (rr.x * misstep)) & 15) + xo, xw0, xw1, HA);
+                        else h_lin(cur + (rr.x - s_lo) * pitch + ((mis0 + (rr.x * misstep)) & 15) + xo, xw0, xw1, HA);
                         rowA = rr.x;
                     }
                     if (rr.y != rowB) {
                         if (rr.y == rowA) { HB[0] = HA[0]; HB[1] = HA[1]; HB[2] = HA[2]; }
-                        else h_lin(cur + (size_t)(rr.y - s_lo) * pitch + ((mis0 + (rr.y * misstep)) & 15) + xo, xw0, xw1, HB);
+                        else h_lin(cur + (rr.y - s_lo) * pitch + ((mis0 + (rr.y * misstep)) & 15) + xo, xw0, xw1, HB);
                         rowB = rr.y;
                     }
                     int o[3];
 #pragma unroll
                     for (int c = 0; c < 3; ++c) o[c] = ((((b0 * HA[c]) >> 16) + ((b1 * HB[c]) >> 16) + 2) >> 2) & 255;
-                    out.px(roi, dy0 + yr, x, o[0], o[1], o[2]);
+                    if (OUT_U8) {
+                        out.px(roi, dy0 + yr, x, o[0], o[1], o[2]);
+                    } else {
+                        float* op = orow + (size_t)yr * T;
+                        op[0] = lut[swap ? o[2] : o[0]];
+                        op[plane] = lut[256 + o[1]];
+                        op[2 * plane] = lut[512 + (swap ? o[0] : o[2])];
+                    }
                 }
-            } else if (incol) {
-                for (int yr = y0; yr < y1; ++yr) out.pad(roi, dy0 + yr, x);
             }
         }
     }
@@ -684,8 +760,6 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
     if (!attr_set[OUT_U8]) {
         cudaError_t e = cudaFuncSetAttribute(bpc_crop_generic_kernel<OUT_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROP_RAW_BYTES);
         if (e != cudaSuccess) return (int)e;
-        e = cudaFuncSetAttribute(bpc_crop_fast_kernel<OUT_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM);
-        if (e != cudaSuccess) return (int)e;
         attr_set[OUT_U8] = true;
     }
     cudaError_t e = cudaMemsetAsync(gcount, 0, 16, st);
@@ -693,8 +767,19 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
     bpc_crop_prep_kernel<<<(R + 127) / 128, 128, 0, st>>>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, geom, glist, gcount, status);
     BPC_LAUNCH_CHECK();
     const uchar4 f4 = make_uchar4(fill[0], fill[1], fill[2], 0);
-    bpc_crop_fast_kernel<OUT_U8><<<R, 256, FAST_SMEM, st>>>(images, B, H, W, geom, R, T, f4, swap_rb, lut, outf, outb);
-    BPC_LAUNCH_CHECK();
+    {
+        typedef void (*FastFn)(const uint8_t*, int, int, int, const RoiGeom*, int, int, uchar4, int, const float*, float*, uint8_t*);
+        const bool aligned = ((long long)W * 3) % 16 == 0;
+        FastFn fn;
+        if (OUT_U8) fn = aligned ? bpc_crop_fast_kernel<OUT_U8, 0, true> : bpc_crop_fast_kernel<OUT_U8, 0, false>;
+        else if (T == 224) fn = aligned ? bpc_crop_fast_kernel<OUT_U8, 224, true> : bpc_crop_fast_kernel<OUT_U8, 224, false>;
+        else if (T == 256) fn = aligned ? bpc_crop_fast_kernel<OUT_U8, 256, true> : bpc_crop_fast_kernel<OUT_U8, 256, false>;
+        else fn = aligned ? bpc_crop_fast_kernel<OUT_U8, 0, true> : bpc_crop_fast_kernel<OUT_U8, 0, false>;
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        fn<<<R, 256, FAST_SMEM, st>>>(images, B, H, W, geom, R, T, f4, swap_rb, lut, outf, outb);
+        BPC_LAUNCH_CHECK();
+    }
     const int nbands = (T + CROP_BAND - 1) / CROP_BAND;
     const long long max_items = (long long)R * nbands;
     const int grid = (int)(max_items < 148 * 4 ? max_items : 148 * 4);
