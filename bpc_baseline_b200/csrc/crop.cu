@@ -8,27 +8,34 @@
 //   regime 3  either axis grows          : 11-bit fixed-point bilinear with area-mode coordinates
 //
 // Three kernels per call:
-//   bpc_crop_prep     one thread per ROI: letterbox geometry (float64, as Python / OpenCV compute it),
-//                     regime, and the class of the ROI (fast / generic / rejected / beyond the count);
-//   bpc_crop_fast     one CTA per ROI, one thread per output column.  Handles regime 1 with scale < 2 on
-//                     both axes (at most 3 taps per axis) and regime 3 -- every box whose long side is
-//                     below 2T.  Source rows of a band of output rows are staged in shared memory with
-//                     16-byte cp.async (double buffered), each thread streams down its column: the
-//                     horizontal pass of a source row is computed once and reused by the two output rows
-//                     that tap it; weights of absent taps are +0.0f, which leaves every float32 sum
-//                     bit-identical (x + 0 == x) while keeping the inner loop branch-free;
+//   bpc_crop_prep     one CTA per ROI: letterbox geometry (float64, as Python / OpenCV compute it), regime
+//                     and class of the ROI, and -- for the fast classes -- the per-column and per-row tap
+//                     descriptors (start index + three float32 weights, absent taps = +0.0f), so that no
+//                     float64 arithmetic is left in the hot kernel;
+//   bpc_crop_warp     persistent CTAs; the unit of work is (ROI, strip of 32 output columns), taken by ONE
+//                     WARP from a global atomic counter, plus one "padding" item per ROI.  A warp stages the
+//                     ~130-byte source segments its strip needs with 16-byte cp.async into its own
+//                     double-buffered slice of shared memory and streams down its strip, one lane per
+//                     column: the horizontal pass of a source row is computed once and reused by the two
+//                     output rows that tap it.  No CTA barrier, no idle warps behind a narrow letterbox.
+//                     Handles regime 1 with scale < 2 on both axes (<= 3 taps per axis) and regime 3, i.e.
+//                     every box whose long side is below 2T;
 //   bpc_crop_generic  persistent CTAs over the (rare) remaining ROIs: any scale, any regime, source rows
 //                     streamed through shared memory in chunks (handles boxes as large as the image).
-// The dominant traffic is the float32 output (3*T*T*4 B per ROI): each warp stores 128 contiguous bytes
-// per plane and row; padding rows are written with 16-byte stores.
+// The dominant traffic is the float32 output (3*T*T*4 B per ROI): each warp stores 128 contiguous bytes per
+// plane and row; padding rows are written with 16-byte stores.
 #include "common.cuh"
 
 namespace bpc {
 
 constexpr int CROP_BAND = 8;                 // generic kernel: output rows per work item
 constexpr int CROP_RAW_BYTES = 40 * 1024;    // generic kernel: staged source bytes
-constexpr int FAST_BUF_BYTES = 20 * 1024;    // fast kernel: one of two staging buffers
-constexpr int FAST_MAX_BAND = 64;
+constexpr int WARP_BUF = 2560;               // warp kernel: bytes of one staging buffer (two per warp)
+constexpr int WARP_DESC = 32 * 16;           // warp kernel: 32 row descriptors (two rings per warp)
+constexpr int WARP_SMEM = 2 * WARP_BUF + 2 * WARP_DESC;
+constexpr int WARPK_WARPS = 8;
+constexpr int WARPK_SMEM = WARPK_WARPS * WARP_SMEM + 768 * 4;
+constexpr int DESC_STRIDE = 256;             // descriptors per ROI and axis (T <= 256)
 
 struct RoiGeom {                             // 88 bytes, workspace
     double scale_x, scale_y, inv_x, inv_y;
@@ -117,61 +124,96 @@ __device__ __forceinline__ void linear_coef(int d, double scale, double inv, int
     w1 = __float2int_rn(__fmul_rn(f, 2048.f));
 }
 
+
 // ------------------------------------------------------------------------------------------------------
-// prep: geometry + classification, one thread per ROI
+// prep: geometry, classification and tap descriptors, one CTA per ROI
 // ------------------------------------------------------------------------------------------------------
-__global__ void bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const int32_t* __restrict__ rois, int R,
-                                     const int32_t* __restrict__ n_rois_dev, int roi_first, int T,
-                                     RoiGeom* __restrict__ geom, int32_t* __restrict__ glist, int32_t* __restrict__ gcount,
-                                     int32_t* __restrict__ status) {
-    const int roi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (roi >= R) return;
-    RoiGeom g;
-    g.scale_x = g.scale_y = g.inv_x = g.inv_y = 0.0;
-    g.src = 0ull;
-    g.new_w = g.new_h = g.dx = g.dy = 0;
-    g.regime = 0; g.cls = 0; g.isx = g.isy = 0; g.pitch = 16; g.pad_ = 0;
-    const int32_t* r = rois + (size_t)roi * 5;
-    const int img = r[0], x1 = r[1], y1 = r[2], x2 = r[3], y2 = r[4];
-    const int w = x2 - x1, h = y2 - y1;
-    g.w = w; g.h = h;
-    if (n_rois_dev != nullptr && roi_first + roi >= *n_rois_dev) {
-        g.cls = -1;
-        geom[roi] = g;
-        return;
-    }
-    if (img >= 0 && img < B && x1 >= 0 && y1 >= 0 && x2 <= W && y2 <= H && w > 0 && h > 0 && w <= BPC_MAX_ROI_WIDTH) {
-        // letterbox geometry, data_utils.py:35-38,41-42 (Python round = half-to-even on the f64 product)
-        const double scale = ddiv((double)T, (double)max(h, w));
-        const int new_w = (int)__double2ll_rn(dmul((double)w, scale));
-        const int new_h = (int)__double2ll_rn(dmul((double)h, scale));
-        if (new_w >= 1 && new_h >= 1 && new_w <= T && new_h <= T) {
-            g.new_w = new_w; g.new_h = new_h;
-            g.dx = (T - new_w) / 2; g.dy = (T - new_h) / 2;
-            g.inv_x = ddiv((double)new_w, (double)w);      // cv2.resize: inv_scale = dsize / ssize
-            g.inv_y = ddiv((double)new_h, (double)h);
-            g.scale_x = ddiv(1.0, g.inv_x);
-            g.scale_y = ddiv(1.0, g.inv_y);
-            if (g.scale_x >= 1.0 && g.scale_y >= 1.0) {
-                g.isx = __double2int_rn(g.scale_x);
-                g.isy = __double2int_rn(g.scale_y);
-                const bool fast = fabs(dsub(g.scale_x, (double)g.isx)) < 2.220446049250313e-16 &&
-                                  fabs(dsub(g.scale_y, (double)g.isy)) < 2.220446049250313e-16;
-                g.regime = fast ? 2 : 1;
-            } else {
-                g.regime = 3;
+// Descriptor formats (float4, DESC_STRIDE per ROI and axis):
+//   class 1 (area, <= 3 taps)  x: (w0, w1, w2, bits(first source column))
+//                              y: (b0, b1, b2, bits(first source row | taps << 24))
+//   class 3 (fixed-point)      x: (bits(w0), bits(w1), 0, bits(source column))      w = 2048, 0 beyond xmax
+//                              y: (bits(b0), bits(b1), bits(second source row), bits(first source row))
+__global__ void __launch_bounds__(256)
+bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const int32_t* __restrict__ rois, int R,
+                     const int32_t* __restrict__ n_rois_dev, int roi_first, int T,
+                     RoiGeom* __restrict__ geom, float4* __restrict__ xdesc, float4* __restrict__ ydesc,
+                     int32_t* __restrict__ glist, int32_t* __restrict__ gcount, int32_t* __restrict__ status) {
+    __shared__ RoiGeom g;
+    const int roi = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        g.scale_x = g.scale_y = g.inv_x = g.inv_y = 0.0;
+        g.src = 0ull;
+        g.new_w = g.new_h = g.dx = g.dy = 0;
+        g.regime = 0; g.cls = 0; g.isx = g.isy = 0; g.pitch = 16; g.pad_ = 0;
+        const int32_t* r = rois + (size_t)roi * 5;
+        const int img = r[0], x1 = r[1], y1 = r[2], x2 = r[3], y2 = r[4];
+        const int w = x2 - x1, h = y2 - y1;
+        g.w = w; g.h = h;
+        if (n_rois_dev != nullptr && roi_first + roi >= *n_rois_dev) {
+            g.cls = -1;
+        } else {
+            if (img >= 0 && img < B && x1 >= 0 && y1 >= 0 && x2 <= W && y2 <= H && w > 0 && h > 0 && w <= BPC_MAX_ROI_WIDTH) {
+                // letterbox geometry, data_utils.py:35-38,41-42 (Python round = half-to-even on the f64 product)
+                const double scale = ddiv((double)T, (double)max(h, w));
+                const int new_w = (int)__double2ll_rn(dmul((double)w, scale));
+                const int new_h = (int)__double2ll_rn(dmul((double)h, scale));
+                if (new_w >= 1 && new_h >= 1 && new_w <= T && new_h <= T) {
+                    g.new_w = new_w; g.new_h = new_h;
+                    g.dx = (T - new_w) / 2; g.dy = (T - new_h) / 2;
+                    g.inv_x = ddiv((double)new_w, (double)w);      // cv2.resize: inv_scale = dsize / ssize
+                    g.inv_y = ddiv((double)new_h, (double)h);
+                    g.scale_x = ddiv(1.0, g.inv_x);
+                    g.scale_y = ddiv(1.0, g.inv_y);
+                    if (g.scale_x >= 1.0 && g.scale_y >= 1.0) {
+                        g.isx = __double2int_rn(g.scale_x);
+                        g.isy = __double2int_rn(g.scale_y);
+                        const bool fast = fabs(dsub(g.scale_x, (double)g.isx)) < 2.220446049250313e-16 &&
+                                          fabs(dsub(g.scale_y, (double)g.isy)) < 2.220446049250313e-16;
+                        g.regime = fast ? 2 : 1;
+                    } else {
+                        g.regime = 3;
+                    }
+                    g.src = (unsigned long long)(uintptr_t)images + (((unsigned long long)img * H + y1) * W + x1) * 3ull;
+                    if (g.regime == 1 && g.scale_x < 2.0 && g.scale_y < 2.0) g.cls = 1;
+                    else if (g.regime == 3) g.cls = 3;
+                    else g.cls = 2;
+                }
             }
-            g.src = (unsigned long long)(uintptr_t)images + (((unsigned long long)img * H + y1) * W + x1) * 3ull;
-            g.pitch = ((3 * w + 15 + 16 + 15) / 16) * 16;   // misalignment + row + slack for zero-weight taps
-            const int rows_fit = FAST_BUF_BYTES / g.pitch;
-            if (g.regime == 1 && g.scale_x < 2.0 && g.scale_y < 2.0 && rows_fit >= 8) g.cls = 1;
-            else if (g.regime == 3 && rows_fit >= 8) g.cls = 3;
-            else g.cls = 2;
+            if (status != nullptr) status[roi] = (g.regime == 0) ? 1 : 0;
+            if (g.cls == 2) glist[atomicAdd(gcount, 1)] = roi;
+        }
+        geom[roi] = g;
+    }
+    __syncthreads();
+    const int cls = g.cls;
+    if (cls != 1 && cls != 3) return;
+    float4* xd = xdesc + (size_t)roi * DESC_STRIDE;
+    float4* yd = ydesc + (size_t)roi * DESC_STRIDE;
+    if (cls == 1) {
+        if (tid < g.new_w) {
+            int xs, xn; float w0, w1, w2;
+            area_taps3(tid, g.scale_x, g.w, xs, xn, w0, w1, w2);
+            xd[tid] = make_float4(w0, w1, w2, __int_as_float(xs));
+        }
+        if (tid < g.new_h) {
+            int ys, yn; float b0, b1, b2;
+            area_taps3(tid, g.scale_y, g.h, ys, yn, b0, b1, b2);
+            yd[tid] = make_float4(b0, b1, b2, __int_as_float(ys | (yn << 24)));
+        }
+    } else {
+        if (tid < g.new_w) {
+            int xs, w0, w1, edge;
+            linear_coef(tid, g.scale_x, g.inv_x, g.w, xs, w0, w1, edge);
+            if (edge) { w0 = 2048; w1 = 0; }                        // D = S[sx] * ONE beyond xmax
+            xd[tid] = make_float4(__int_as_float(w0), __int_as_float(w1), 0.f, __int_as_float(xs));
+        }
+        if (tid < g.new_h) {
+            int s0, b0, b1, edge;
+            linear_coef(tid, g.scale_y, g.inv_y, g.h, s0, b0, b1, edge);
+            const int s1 = min(s0 + 1, g.h - 1);
+            yd[tid] = make_float4(__int_as_float(b0), __int_as_float(b1), __int_as_float(s1), __int_as_float(s0));
         }
     }
-    if (status != nullptr) status[roi] = (g.regime == 0) ? 1 : 0;
-    if (g.cls == 2) glist[atomicAdd(gcount, 1)] = roi;
-    geom[roi] = g;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -238,34 +280,11 @@ __device__ __forceinline__ void out_init(Out<OUT_U8>& o, float* outf, uint8_t* o
         for (int p = 0; p < 3; ++p) o.padf[p] = lut_s[p * 256 + o.fillc[swap_rb ? 2 - p : p]];
 }
 
-// ------------------------------------------------------------------------------------------------------
-// fast kernel
-// ------------------------------------------------------------------------------------------------------
-// stage source rows [s_lo, s_lo + count) of the ROI into buf (16-byte cp.async of the aligned superset)
-__device__ __forceinline__ void fast_stage(unsigned char* buf, unsigned long long src0, unsigned long long rowstride,
-                                           unsigned long long img_end, int s_lo, int count, int pitch, int w, int tid) {
-    const int lane = tid & 31, wid = tid >> 5;
-    for (int r = wid; r < count; r += 8) {
-        const unsigned long long ga = src0 + (unsigned long long)(s_lo + r) * rowstride;
-        const unsigned long long al16 = ga & ~15ull;
-        const int need = (int)(ga - al16) + 3 * w + 8;             // + slack read by zero-weight taps
-        unsigned char* dst = buf + (size_t)r * pitch;
-        for (int v = lane; v * 16 < need; v += 32) {
-            const unsigned long long a = al16 + (unsigned long long)v * 16ull;
-            if (a + 16ull <= img_end) {
-                cp_async16(dst + v * 16, (const void*)(uintptr_t)a);
-            } else {                                               // last bytes of the image pool
-                unsigned int tmp[4] = {0u, 0u, 0u, 0u};
-                for (int b = 0; b < 16; ++b)
-                    if (a + b < img_end) tmp[b >> 2] |= (unsigned int)(*(const uint8_t*)(uintptr_t)(a + b)) << (8 * (b & 3));
-                *reinterpret_cast<uint4*>(dst + v * 16) = make_uint4(tmp[0], tmp[1], tmp[2], tmp[3]);
-            }
-        }
-    }
-    cp_async_commit();
-}
 
-// ---- packed float32x2 arithmetic (sm_100a FFMA2 / FADD2 / FMUL2), every lane IEEE round-to-nearest ----
+// ------------------------------------------------------------------------------------------------------
+// warp kernel: (ROI, 32-column strip) items, one warp each
+// ------------------------------------------------------------------------------------------------------
+// ---- packed float32x2 arithmetic (sm_100a FFMA2 / FADD2), every lane IEEE round-to-nearest ----
 typedef unsigned long long u64;
 __device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
@@ -279,7 +298,7 @@ __device__ __forceinline__ u64 fadd2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0
 // non-negative operands, and an FFMA2 cannot be merged with the add that follows.
 __device__ __forceinline__ u64 fprod2(u64 a, u64 b, u64 negzero2) { return ffma2(a, b, negzero2); }
 
-// float(2^23 + byte k of v): the byte dropped into the mantissa of 8388608.0f (one PRMT, no I2F)
+// float(2^23 + byte K of v): the byte dropped into the mantissa of 8388608.0f (one PRMT, no I2F)
 template <int K>
 __device__ __forceinline__ float magic_byte(unsigned v) { return __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540 + K)); }
 
@@ -299,7 +318,7 @@ struct ColW {
     }
 };
 
-// horizontal pass of one source row for one output column: 9 bytes starting at byte offset (a4 + sh/8)
+// horizontal pass of one source row for one output column: 9 bytes starting at byte offset a4 + sh/8
 __device__ __forceinline__ void h_area3(const unsigned char* __restrict__ base, int a4, int sh, const ColW& cw, u64& h01, float& h2) {
     const unsigned q0 = *reinterpret_cast<const unsigned*>(base + a4);
     const unsigned q1 = *reinterpret_cast<const unsigned*>(base + a4 + 4);
@@ -316,208 +335,257 @@ __device__ __forceinline__ void h_area3(const unsigned char* __restrict__ base, 
     h2 = __fadd_rn(__fadd_rn(r0, r1), r2);
 }
 
-__device__ __forceinline__ void h_lin(const uint8_t* __restrict__ p, int w0, int w1, int* h) {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) h[c] = ((int)p[c] * w0 + (int)p[3 + c] * w1) >> 4;
+// horizontal pass of the fixed-point bilinear: 6 bytes at byte offset a4 + sh/8, result pre-shifted by 4
+__device__ __forceinline__ void h_lin(const unsigned char* __restrict__ base, int a4, int sh, int w0, int w1, int* h) {
+    const unsigned q0 = *reinterpret_cast<const unsigned*>(base + a4);
+    const unsigned q1 = *reinterpret_cast<const unsigned*>(base + a4 + 4);
+    const unsigned q2 = *reinterpret_cast<const unsigned*>(base + a4 + 8);
+    const unsigned v0 = __funnelshift_r(q0, q1, sh), v1 = __funnelshift_r(q1, q2, sh);
+    h[0] = (int)((v0 & 0xffu) * w0 + (v0 >> 24) * w1) >> 4;
+    h[1] = (int)(((v0 >> 8) & 0xffu) * w0 + (v1 & 0xffu) * w1) >> 4;
+    h[2] = (int)(((v0 >> 16) & 0xffu) * w0 + ((v1 >> 8) & 0xffu) * w1) >> 4;
 }
 
 // cvRound(v) for 0 <= v < 2^22 without F2I: adding 2^23 leaves round-half-even(v) in the low mantissa bits
 __device__ __forceinline__ int round_u8(float v) { return min(255, __float_as_int(__fadd_rn(v, 8388608.0f)) & 0x1ff); }
 
+// 16-byte cp.async of rows [s_lo, s_lo + count) of a strip; lane (lr, lv) copies vector lv of rows lr, lr + rpp, ...
+__device__ __forceinline__ void warp_stage(unsigned char* buf, unsigned long long src_seg, unsigned long long rowstride,
+                                           unsigned long long img_end, int s_lo, int count, int pitch, int lr, int lv, int rpp) {
+    if (lr < rpp) {
+        for (int r = lr; r < count; r += rpp) {
+            const unsigned long long ga = src_seg + (unsigned long long)(s_lo + r) * rowstride;
+            const unsigned long long a = (ga & ~15ull) + (unsigned long long)lv * 16ull;
+            unsigned char* dst = buf + r * pitch + lv * 16;
+            if (a + 16ull <= img_end) {
+                cp_async16(dst, (const void*)(uintptr_t)a);
+            } else {                                               // last bytes of the image pool
+                unsigned int tmp[4] = {0u, 0u, 0u, 0u};
+                for (int b = 0; b < 16; ++b)
+                    if (a + b < img_end) tmp[b >> 2] |= (unsigned int)(*(const uint8_t*)(uintptr_t)(a + b)) << (8 * (b & 3));
+                *reinterpret_cast<uint4*>(dst) = make_uint4(tmp[0], tmp[1], tmp[2], tmp[3]);
+            }
+        }
+    }
+    cp_async_commit();
+}
+
+__device__ __forceinline__ int warp_max_i32(int v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, m));
+    return v;
+}
+
 // TT = compile-time target size (0: run-time T); ALIGNED = the image row pitch W*3 is a multiple of 16 bytes
 template <bool OUT_U8, int TT, bool ALIGNED>
-__global__ void __launch_bounds__(256, 3)
-bpc_crop_fast_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom, int R,
-                     int Trt, uchar4 fill, int swap_rb, const float* __restrict__ lut_g,
+__global__ void __launch_bounds__(256, 4)
+bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom,
+                     const float4* __restrict__ xdesc, const float4* __restrict__ ydesc, int32_t* __restrict__ wcount,
+                     int R, int Trt, int nslot, uchar4 fill, int swap_rb, const float* __restrict__ lut_g,
                      float* __restrict__ outf, uint8_t* __restrict__ outb) {
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned char* buf0 = smem;
-    unsigned char* buf1 = smem + FAST_BUF_BYTES;
-    float4* ydw = reinterpret_cast<float4*>(smem + 2 * FAST_BUF_BYTES);          // [256] weights (+ n in .w)
-    int2* yds = reinterpret_cast<int2*>(smem + 2 * FAST_BUF_BYTES + 256 * 16);    // [256] first / last source row
-    float* lut = reinterpret_cast<float*>(smem + 2 * FAST_BUF_BYTES + 256 * 24);  // [768]
-
+    float* lut = reinterpret_cast<float*>(smem);                                 // [768]
     const int T = TT ? TT : Trt;
-    const int tid = threadIdx.x;
-    const int roi = blockIdx.x;
-    const RoiGeom* gp = geom + roi;
-    const int cls = gp->cls;
-    if (cls == -1 || cls == 2) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned char* wbase = smem + 768 * 4 + wid * WARP_SMEM;          // [2][WARP_BUF] staging, then [2][32] float4 row descriptors
+
     if (!OUT_U8)
         for (int e = tid; e < 768; e += 256) lut[e] = lut_g[e];
     __syncthreads();
     Out<OUT_U8> out;
     out_init(out, outf, outb, lut, T, swap_rb, fill);
-    if (cls == 0) { out.pad_rows(roi, 0, T, tid, 256); return; }
-
-    const int w = gp->w, h = gp->h, new_w = gp->new_w, new_h = gp->new_h, dx0 = gp->dx, dy0 = gp->dy, pitch = gp->pitch;
-    const double scale_x = gp->scale_x, scale_y = gp->scale_y;
-    const unsigned long long src0 = gp->src;
+    const bool swap = swap_rb != 0;
+    const size_t plane = (size_t)T * T;
     const unsigned long long rowstride = (unsigned long long)W * 3ull;
     const unsigned long long img_end = (unsigned long long)(uintptr_t)images + (unsigned long long)B * H * rowstride;
-    const int mis0 = (int)(src0 & 15ull), misstep = ALIGNED ? 0 : (int)(rowstride & 15ull);
+    const float nz = __int_as_float((int)(0x80000000u | (unsigned)fill.w));     // -0.0f: fill.w is 0 at run time
+    const u64 nz2 = pack2(nz, nz);
+    const long long nitems = (long long)R * nslot;
 
-    // letterbox padding: whole rows above / below, column strips left / right of the resized image
-    out.pad_rows(roi, 0, dy0, tid, 256);
-    out.pad_rows(roi, dy0 + new_h, T, tid, 256);
-    {
-        const int npc = T - new_w;
-        if (npc > 0)
-            for (int r = tid >> 5; r < new_h; r += 8)
-                for (int c = tid & 31; c < npc; c += 32) out.pad(roi, dy0 + r, c < dx0 ? c : c + new_w);
-    }
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(wcount, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nitems) break;
+        const int roi = item / nslot, slot = item - roi * nslot;
+        const RoiGeom* gp = geom + roi;
+        const int cls = gp->cls;
+        if (cls == -1 || cls == 2) continue;
+        const int new_w = gp->new_w, new_h = gp->new_h, dx0 = gp->dx, dy0 = gp->dy;
 
-    const int x = tid, xr = x - dx0;
-    const bool active = x < T && xr >= 0 && xr < new_w;
-    const int rows_fit = FAST_BUF_BYTES / pitch;
-    const bool swap = swap_rb != 0;
-    // per-thread output pointer of (plane 0, row dy0, column x); advanced by T per output row
-    float* orow = outf + ((size_t)roi * 3 * T + dy0) * T + x;
-    const size_t plane = (size_t)T * T;
-
-    if (cls == 1) {
-        // ---------------- regime 1, at most 3 taps per axis ----------------
-        int xs = 0, xn = 0;
-        ColW cw;
-        {
-            float w0 = 0.f, w1 = 0.f, w2 = 0.f;
-            if (active) area_taps3(xr, scale_x, w, xs, xn, w0, w1, w2);
-            cw.set(w0, w1, w2);
-        }
-        if (tid < new_h) {
-            int ys, yn; float b0, b1, b2;
-            area_taps3(tid, scale_y, h, ys, yn, b0, b1, b2);
-            ydw[tid] = make_float4(b0, b1, b2, __int_as_float(yn));
-            yds[tid] = make_int2(ys, ys + yn - 1);
-        }
-        __syncthreads();
-        const int band_h = max(1, min(FAST_MAX_BAND, (int)((double)(rows_fit - 3) / scale_y)));
-        const int nb = (new_h + band_h - 1) / band_h;
-        const int colc = 3 * xs + (ALIGNED ? mis0 : 0);          // byte offset of the column inside a staged row
-        int crow = -1;
-        const float nz = __int_as_float((int)(0x80000000u | (unsigned)fill.w));     // -0.0f: fill.w is 0 at run time
-        const u64 nz2 = pack2(nz, nz);
-        u64 hc01 = 0ull;
-        float hc2 = 0.f;
-        {
-            const int y1 = min(new_h, band_h);
-            const int s_lo = yds[0].x, s_hi = yds[y1 - 1].y;
-            fast_stage(buf0, src0, rowstride, img_end, s_lo, s_hi - s_lo + 1, pitch, w, tid);
-        }
-        for (int b = 0; b < nb; ++b) {
-            const unsigned char* cur = (b & 1) ? buf1 : buf0;
-            cp_async_wait_all();
-            __syncthreads();
-            if (b + 1 < nb) {
-                const int y0n = (b + 1) * band_h, y1n = min(new_h, y0n + band_h);
-                const int s_lo = yds[y0n].x, s_hi = yds[y1n - 1].y;
-                fast_stage((b & 1) ? buf0 : buf1, src0, rowstride, img_end, s_lo, s_hi - s_lo + 1, pitch, w, tid);
+        if (slot == nslot - 1) {
+            // ---------------- padding item: rows above / below and column strips left / right ----------------
+            if (cls == 0) { out.pad_rows(roi, 0, T, lane, 32); continue; }
+            out.pad_rows(roi, 0, dy0, lane, 32);
+            out.pad_rows(roi, dy0 + new_h, T, lane, 32);
+            // 32-column strips that do not touch the resized image (the others pad their own lanes)
+            for (int c = 0; c * 32 < T; ++c) {
+                if (c * 32 < dx0 + new_w && c * 32 + 32 > dx0) continue;
+                const int x = c * 32 + lane;
+                if (x < T)
+                    for (int r = 0; r < new_h; ++r) out.pad(roi, dy0 + r, x);
             }
-            const int y0 = b * band_h, y1 = min(new_h, y0 + band_h);
-            const int s_lo = yds[y0].x;
-            if (active) {
-                for (int yr = y0; yr < y1; ++yr) {
-                    const float4 d = ydw[yr];
-                    const int ys = yds[yr].x;
-                    const int n = __float_as_int(d.w);
-                    int a = (ys - s_lo) * pitch + colc;
-                    if (!ALIGNED) a += (mis0 + ys * misstep) & 15;
-                    if (ys != crow) h_area3(cur, a & ~3, (a & 3) * 8, cw, hc01, hc2);
-                    u64 acc01 = fprod2(pack2(d.x, d.x), hc01, nz2);
-                    float acc2 = __fmul_rn(d.x, hc2);
-                    if (n > 1) {
-                        int a1 = a + pitch;
-                        if (!ALIGNED) a1 = (ys + 1 - s_lo) * pitch + colc + ((mis0 + (ys + 1) * misstep) & 15);
-                        h_area3(cur, a1 & ~3, (a1 & 3) * 8, cw, hc01, hc2);
-                        acc01 = fadd2(acc01, fprod2(pack2(d.y, d.y), hc01, nz2));
-                        acc2 = __fadd_rn(acc2, __fmul_rn(d.y, hc2));
+            continue;
+        }
+        if (cls == 0 || slot * 32 >= dx0 + new_w || slot * 32 + 32 <= dx0) continue;
+
+        // ---------------- output columns [32 slot, 32 slot + 32): full 128-byte lines per plane and row ----------------
+        const int x = slot * 32 + lane;
+        const int xr = x - dx0;
+        const bool active = xr >= 0 && xr < new_w;
+        const bool padlane = !active && x < T;
+        const float4 xd = xdesc[(size_t)roi * DESC_STRIDE + min(max(xr, 0), new_w - 1)];
+        const int xs = __float_as_int(xd.w);
+        const int xs_min = -warp_max_i32(-xs);
+        const int xs_max = warp_max_i32(xs);
+        const int seg_bytes = 3 * (xs_max + 3 - xs_min);
+        const int pitch = ((15 + seg_bytes + 8 + 15) >> 4) << 4;
+        const int nv = pitch >> 4;
+        const int rpp = 32 / nv, lr = lane / nv, lv = lane - lr * nv;
+        const unsigned long long src_seg = gp->src + 3ull * (unsigned long long)xs_min;
+        const int mis0 = (int)(src_seg & 15ull), misstep = ALIGNED ? 0 : (int)(rowstride & 15ull);
+        const int colc = 3 * (xs - xs_min) + (ALIGNED ? mis0 : 0);
+        const int rows_fit = WARP_BUF / pitch;
+        const double scale_y = gp->scale_y;
+        const int bh = max(1, min(32, (int)((double)(rows_fit - 3) / (scale_y < 1.0 ? 1.0 : scale_y))));
+        const int nb = (new_h + bh - 1) / bh;
+        const float4* ydr = ydesc + (size_t)roi * DESC_STRIDE;
+        float* orow = outf + ((size_t)roi * 3 * T + dy0) * T + x;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        // descriptors of batch b (rows b*bh ..) -> ring k, source rows -> buffer k; returns the first source row
+        auto stage = [&](int b, int k, const float4& yd) -> int {
+            const int cnt = min(bh, new_h - b * bh);
+            if (lane < cnt) reinterpret_cast<float4*>(wbase + 2 * WARP_BUF + k * WARP_DESC)[lane] = yd;
+            int lo, hi;
+            if (cls == 1) {
+                const int ysn = __float_as_int(yd.w);
+                lo = ysn & 0xffffff; hi = lo + (ysn >> 24) - 1;
+            } else {
+                lo = __float_as_int(yd.w); hi = __float_as_int(yd.z);
+            }
+            const int s_lo = __shfl_sync(0xffffffffu, lo, 0);
+            const int s_hi = __shfl_sync(0xffffffffu, hi, cnt - 1);
+            warp_stage(wbase + k * WARP_BUF, src_seg, rowstride, img_end, s_lo, s_hi - s_lo + 1, pitch, lr, lv, rpp);
+            return s_lo;
+        };
+        auto load_desc = [&](int b) -> float4 {
+            const int y = b * bh + lane;
+            return (b < nb && y < new_h && lane < bh) ? ydr[y] : zero4;
+        };
+
+        __syncwarp();                                   // previous item finished with the buffers
+        int s_lo_cur = stage(0, 0, load_desc(0));
+        float4 ydn = load_desc(1);
+        int s_lo_next = 0;
+
+        if (cls == 1) {
+            ColW cw;
+            cw.set(xd.x, xd.y, xd.z);
+            int crow = -1;
+            u64 hc01 = 0ull;
+            float hc2 = 0.f;
+            for (int b = 0; b < nb; ++b) {
+                const int k = b & 1;
+                cp_async_wait_all();
+                __syncwarp();
+                if (b + 1 < nb) s_lo_next = stage(b + 1, k ^ 1, ydn);
+                ydn = load_desc(b + 2);
+                const unsigned char* cur = wbase + k * WARP_BUF;
+                const float4* ring = reinterpret_cast<const float4*>(wbase + 2 * WARP_BUF + k * WARP_DESC);
+                const int y0 = b * bh, cnt = min(bh, new_h - y0);
+                if (active) {
+                    for (int r = 0; r < cnt; ++r) {
+                        const float4 d = ring[r];
+                        const int ysn = __float_as_int(d.w);
+                        const int ys = ysn & 0xffffff, n = ysn >> 24;
+                        int a = (ys - s_lo_cur) * pitch + colc;
+                        if (!ALIGNED) a += (mis0 + ys * misstep) & 15;
+                        if (ys != crow) h_area3(cur, a & ~3, (a & 3) * 8, cw, hc01, hc2);
+                        u64 acc01 = fprod2(pack2(d.x, d.x), hc01, nz2);
+                        float acc2 = __fmul_rn(d.x, hc2);
+                        if (n > 1) {
+                            int a1 = a + pitch;
+                            if (!ALIGNED) a1 = (ys + 1 - s_lo_cur) * pitch + colc + ((mis0 + (ys + 1) * misstep) & 15);
+                            h_area3(cur, a1 & ~3, (a1 & 3) * 8, cw, hc01, hc2);
+                            acc01 = fadd2(acc01, fprod2(pack2(d.y, d.y), hc01, nz2));
+                            acc2 = __fadd_rn(acc2, __fmul_rn(d.y, hc2));
+                        }
+                        if (n > 2) {
+                            int a2 = a + 2 * pitch;
+                            if (!ALIGNED) a2 = (ys + 2 - s_lo_cur) * pitch + colc + ((mis0 + (ys + 2) * misstep) & 15);
+                            h_area3(cur, a2 & ~3, (a2 & 3) * 8, cw, hc01, hc2);
+                            acc01 = fadd2(acc01, fprod2(pack2(d.z, d.z), hc01, nz2));
+                            acc2 = __fadd_rn(acc2, __fmul_rn(d.z, hc2));
+                        }
+                        crow = ys + n - 1;
+                        float a0f, a1f;
+                        unpack2(acc01, a0f, a1f);
+                        const int o0 = round_u8(a0f), o1 = round_u8(a1f), o2 = round_u8(acc2);
+                        if (OUT_U8) {
+                            out.px(roi, dy0 + y0 + r, x, o0, o1, o2);
+                        } else {
+                            float* o = orow + (size_t)(y0 + r) * T;
+                            o[0] = lut[swap ? o2 : o0];
+                            o[plane] = lut[256 + o1];
+                            o[2 * plane] = lut[512 + (swap ? o0 : o2)];
+                        }
                     }
-                    if (n > 2) {
-                        int a2 = a + 2 * pitch;
-                        if (!ALIGNED) a2 = (ys + 2 - s_lo) * pitch + colc + ((mis0 + (ys + 2) * misstep) & 15);
-                        h_area3(cur, a2 & ~3, (a2 & 3) * 8, cw, hc01, hc2);
-                        acc01 = fadd2(acc01, fprod2(pack2(d.z, d.z), hc01, nz2));
-                        acc2 = __fadd_rn(acc2, __fmul_rn(d.z, hc2));
-                    }
-                    crow = ys + n - 1;
-                    float a0f, a1f;
-                    unpack2(acc01, a0f, a1f);
-                    const int o0 = round_u8(a0f), o1 = round_u8(a1f), o2 = round_u8(acc2);
-                    if (OUT_U8) {
-                        out.px(roi, dy0 + yr, x, o0, o1, o2);
-                    } else {
-                        float* o = orow + (size_t)yr * T;
-                        o[0] = lut[swap ? o2 : o0];
-                        o[plane] = lut[256 + o1];
-                        o[2 * plane] = lut[512 + (swap ? o0 : o2)];
-                    }
+                } else if (padlane) {
+                    for (int r = 0; r < cnt; ++r) out.pad(roi, dy0 + y0 + r, x);
                 }
+                s_lo_cur = s_lo_next;
             }
-        }
-    } else {
-        // ---------------- regime 3: fixed-point bilinear ----------------
-        int xs = 0, xw0 = 0, xw1 = 0, xedge = 0;
-        if (active) {
-            linear_coef(xr, scale_x, gp->inv_x, w, xs, xw0, xw1, xedge);
-            if (xedge) { xw0 = 2048; xw1 = 0; }                    // D = S[sx] * ONE beyond xmax
-        }
-        if (tid < new_h) {
-            int s0, b0, b1, edge;
-            linear_coef(tid, scale_y, gp->inv_y, h, s0, b0, b1, edge);
-            const int s1 = min(s0 + 1, h - 1);
-            ydw[tid] = make_float4(__int_as_float(b0), __int_as_float(b1), 0.f, 0.f);
-            yds[tid] = make_int2(s0, s1);
-        }
-        __syncthreads();
-        const double sy_eff = scale_y < 1.0 ? 1.0 : scale_y;
-        const int band_h = max(1, min(FAST_MAX_BAND, (int)((double)(rows_fit - 3) / sy_eff)));
-        const int nb = (new_h + band_h - 1) / band_h;
-        const int xo = 3 * xs;
-        int rowA = -1, rowB = -1;
-        int HA[3] = {0, 0, 0}, HB[3] = {0, 0, 0};
-        {
-            const int y1 = min(new_h, band_h);
-            const int s_lo = yds[0].x, s_hi = yds[y1 - 1].y;
-            fast_stage(buf0, src0, rowstride, img_end, s_lo, s_hi - s_lo + 1, pitch, w, tid);
-        }
-        for (int b = 0; b < nb; ++b) {
-            const unsigned char* cur = (b & 1) ? buf1 : buf0;
-            cp_async_wait_all();
-            __syncthreads();
-            if (b + 1 < nb) {
-                const int y0n = (b + 1) * band_h, y1n = min(new_h, y0n + band_h);
-                const int s_lo = yds[y0n].x, s_hi = yds[y1n - 1].y;
-                fast_stage((b & 1) ? buf0 : buf1, src0, rowstride, img_end, s_lo, s_hi - s_lo + 1, pitch, w, tid);
-            }
-            const int y0 = b * band_h, y1 = min(new_h, y0 + band_h);
-            const int s_lo = yds[y0].x;
-            if (active) {
-                for (int yr = y0; yr < y1; ++yr) {
-                    const float4 d = ydw[yr];
-                    const int2 rr = yds[yr];
-                    const int b0 = __float_as_int(d.x), b1 = __float_as_int(d.y);
-                    if (rr.x != rowA) {
-                        if (rr.x == rowB) { HA[0] = HB[0]; HA[1] = HB[1]; HA[2] = HB[2]; }
-                        else h_lin(cur + (rr.x - s_lo) * pitch + ((mis0 + (rr.x * misstep)) & 15) + xo, xw0, xw1, HA);
-                        rowA = rr.x;
-                    }
-                    if (rr.y != rowB) {
-                        if (rr.y == rowA) { HB[0] = HA[0]; HB[1] = HA[1]; HB[2] = HA[2]; }
-                        else h_lin(cur + (rr.y - s_lo) * pitch + ((mis0 + (rr.y * misstep)) & 15) + xo, xw0, xw1, HB);
-                        rowB = rr.y;
-                    }
-                    int o[3];
+        } else {
+            const int xw0 = __float_as_int(xd.x), xw1 = __float_as_int(xd.y);
+            int rowA = -1, rowB = -1;
+            int HA[3] = {0, 0, 0}, HB[3] = {0, 0, 0};
+            for (int b = 0; b < nb; ++b) {
+                const int k = b & 1;
+                cp_async_wait_all();
+                __syncwarp();
+                if (b + 1 < nb) s_lo_next = stage(b + 1, k ^ 1, ydn);
+                ydn = load_desc(b + 2);
+                const unsigned char* cur = wbase + k * WARP_BUF;
+                const float4* ring = reinterpret_cast<const float4*>(wbase + 2 * WARP_BUF + k * WARP_DESC);
+                const int y0 = b * bh, cnt = min(bh, new_h - y0);
+                if (active) {
+                    for (int r = 0; r < cnt; ++r) {
+                        const float4 d = ring[r];
+                        const int b0 = __float_as_int(d.x), b1 = __float_as_int(d.y);
+                        const int sy0 = __float_as_int(d.w), sy1 = __float_as_int(d.z);
+                        if (sy0 != rowA) {
+                            if (sy0 == rowB) { HA[0] = HB[0]; HA[1] = HB[1]; HA[2] = HB[2]; }
+                            else {
+                                const int a = (sy0 - s_lo_cur) * pitch + colc + (ALIGNED ? 0 : ((mis0 + sy0 * misstep) & 15));
+                                h_lin(cur, a & ~3, (a & 3) * 8, xw0, xw1, HA);
+                            }
+                            rowA = sy0;
+                        }
+                        if (sy1 != rowB) {
+                            if (sy1 == rowA) { HB[0] = HA[0]; HB[1] = HA[1]; HB[2] = HA[2]; }
+                            else {
+                                const int a = (sy1 - s_lo_cur) * pitch + colc + (ALIGNED ? 0 : ((mis0 + sy1 * misstep) & 15));
+                                h_lin(cur, a & ~3, (a & 3) * 8, xw0, xw1, HB);
+                            }
+                            rowB = sy1;
+                        }
+                        int o[3];
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) o[c] = ((((b0 * HA[c]) >> 16) + ((b1 * HB[c]) >> 16) + 2) >> 2) & 255;
-                    if (OUT_U8) {
-                        out.px(roi, dy0 + yr, x, o[0], o[1], o[2]);
-                    } else {
-                        float* op = orow + (size_t)yr * T;
-                        op[0] = lut[swap ? o[2] : o[0]];
-                        op[plane] = lut[256 + o[1]];
-                        op[2 * plane] = lut[512 + (swap ? o[0] : o[2])];
+                        for (int c = 0; c < 3; ++c) o[c] = ((((b0 * HA[c]) >> 16) + ((b1 * HB[c]) >> 16) + 2) >> 2) & 255;
+                        if (OUT_U8) {
+                            out.px(roi, dy0 + y0 + r, x, o[0], o[1], o[2]);
+                        } else {
+                            float* op = orow + (size_t)(y0 + r) * T;
+                            op[0] = lut[swap ? o[2] : o[0]];
+                            op[plane] = lut[256 + o[1]];
+                            op[2 * plane] = lut[512 + (swap ? o[0] : o[2])];
+                        }
                     }
+                } else if (padlane) {
+                    for (int r = 0; r < cnt; ++r) out.pad(roi, dy0 + y0 + r, x);
                 }
+                s_lo_cur = s_lo_next;
             }
         }
     }
@@ -737,11 +805,11 @@ __global__ void bpc_lut_kernel(float m0, float m1, float m2, float s0, float s1,
     lut[t] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), mean), sd);
 }
 
-static size_t crop_workspace_bytes(int R) {
-    return (size_t)R * sizeof(RoiGeom) + ((size_t)R + 4) * sizeof(int32_t) + 64;
-}
-
-constexpr int FAST_SMEM = 2 * FAST_BUF_BYTES + 256 * 24 + 768 * 4;
+// workspace: geom[R] | xdesc[R][256] | ydesc[R][256] | counters[16] | glist[R]
+static size_t ws_off_xdesc(int R) { return (((size_t)R * sizeof(RoiGeom)) + 15) & ~(size_t)15; }
+static size_t ws_off_ydesc(int R) { return ws_off_xdesc(R) + (size_t)R * DESC_STRIDE * sizeof(float4); }
+static size_t ws_off_count(int R) { return ws_off_ydesc(R) + (size_t)R * DESC_STRIDE * sizeof(float4); }
+static size_t crop_workspace_bytes(int R) { return ws_off_count(R) + 64 + (size_t)R * sizeof(int32_t) + 64; }
 
 template <bool OUT_U8>
 static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R, const int32_t* n_rois_dev,
@@ -752,37 +820,47 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
     if (((uintptr_t)images & 15) != 0 || ((uintptr_t)workspace & 15) != 0) return BPC_EALIGN;
     if (R == 0) return BPC_OK;
     if (workspace_bytes < crop_workspace_bytes(R)) return BPC_EWORKSPACE;
+    const int nslot = (T + 31) / 32 + 1;
+    if ((long long)R * nslot > 0x7fffffffLL) return BPC_ETOOBIG;
     cudaStream_t st = (cudaStream_t)stream;
-    RoiGeom* geom = (RoiGeom*)workspace;
-    int32_t* gcount = (int32_t*)((unsigned char*)workspace + (size_t)R * sizeof(RoiGeom));
-    int32_t* glist = gcount + 4;
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[OUT_U8]) {
-        cudaError_t e = cudaFuncSetAttribute(bpc_crop_generic_kernel<OUT_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROP_RAW_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        attr_set[OUT_U8] = true;
-    }
-    cudaError_t e = cudaMemsetAsync(gcount, 0, 16, st);
+    unsigned char* wsb = (unsigned char*)workspace;
+    RoiGeom* geom = (RoiGeom*)wsb;
+    float4* xdesc = (float4*)(wsb + ws_off_xdesc(R));
+    float4* ydesc = (float4*)(wsb + ws_off_ydesc(R));
+    int32_t* gcount = (int32_t*)(wsb + ws_off_count(R));      // [0] generic-list length, [4] warp-item counter
+    int32_t* wcount = gcount + 4;
+    int32_t* glist = gcount + 16;
+    cudaError_t e = cudaMemsetAsync(gcount, 0, 64, st);
     if (e != cudaSuccess) return (int)e;
-    bpc_crop_prep_kernel<<<(R + 127) / 128, 128, 0, st>>>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, geom, glist, gcount, status);
+    bpc_crop_prep_kernel<<<R, 256, 0, st>>>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, geom, xdesc, ydesc, glist, gcount, status);
     BPC_LAUNCH_CHECK();
     const uchar4 f4 = make_uchar4(fill[0], fill[1], fill[2], 0);
     {
-        typedef void (*FastFn)(const uint8_t*, int, int, int, const RoiGeom*, int, int, uchar4, int, const float*, float*, uint8_t*);
+        typedef void (*WarpFn)(const uint8_t*, int, int, int, const RoiGeom*, const float4*, const float4*, int32_t*, int, int, int,
+                               uchar4, int, const float*, float*, uint8_t*);
         const bool aligned = ((long long)W * 3) % 16 == 0;
-        FastFn fn;
-        if (OUT_U8) fn = aligned ? bpc_crop_fast_kernel<OUT_U8, 0, true> : bpc_crop_fast_kernel<OUT_U8, 0, false>;
-        else if (T == 224) fn = aligned ? bpc_crop_fast_kernel<OUT_U8, 224, true> : bpc_crop_fast_kernel<OUT_U8, 224, false>;
-        else if (T == 256) fn = aligned ? bpc_crop_fast_kernel<OUT_U8, 256, true> : bpc_crop_fast_kernel<OUT_U8, 256, false>;
-        else fn = aligned ? bpc_crop_fast_kernel<OUT_U8, 0, true> : bpc_crop_fast_kernel<OUT_U8, 0, false>;
-        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, FAST_SMEM);
+        WarpFn fn;
+        if (OUT_U8) fn = aligned ? bpc_crop_warp_kernel<OUT_U8, 0, true> : bpc_crop_warp_kernel<OUT_U8, 0, false>;
+        else if (T == 224) fn = aligned ? bpc_crop_warp_kernel<OUT_U8, 224, true> : bpc_crop_warp_kernel<OUT_U8, 224, false>;
+        else if (T == 256) fn = aligned ? bpc_crop_warp_kernel<OUT_U8, 256, true> : bpc_crop_warp_kernel<OUT_U8, 256, false>;
+        else fn = aligned ? bpc_crop_warp_kernel<OUT_U8, 0, true> : bpc_crop_warp_kernel<OUT_U8, 0, false>;
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, WARPK_SMEM);
         if (e != cudaSuccess) return (int)e;
-        fn<<<R, 256, FAST_SMEM, st>>>(images, B, H, W, geom, R, T, f4, swap_rb, lut, outf, outb);
+        const long long nitems = (long long)R * nslot;
+        const long long want = (nitems + WARPK_WARPS - 1) / WARPK_WARPS;
+        const int grid = (int)(want < 148 * 4 ? want : 148 * 4);
+        fn<<<grid, 256, WARPK_SMEM, st>>>(images, B, H, W, geom, xdesc, ydesc, wcount, R, T, nslot, f4, swap_rb, lut, outf, outb);
         BPC_LAUNCH_CHECK();
+    }
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[OUT_U8]) {
+        e = cudaFuncSetAttribute(bpc_crop_generic_kernel<OUT_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROP_RAW_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        attr_set[OUT_U8] = true;
     }
     const int nbands = (T + CROP_BAND - 1) / CROP_BAND;
     const long long max_items = (long long)R * nbands;
-    const int grid = (int)(max_items < 148 * 4 ? max_items : 148 * 4);
+    const int grid = (int)(max_items < 148 * 2 ? max_items : 148 * 2);
     const int threads = ((T + 31) / 32) * 32;
     bpc_crop_generic_kernel<OUT_U8><<<grid, threads, CROP_RAW_BYTES, st>>>(images, B, H, W, geom, glist, gcount, T, nbands, f4, swap_rb, lut, outf, outb);
     BPC_LAUNCH_CHECK();
