@@ -306,40 +306,41 @@ __device__ __forceinline__ float magic_byte(unsigned v) { return __uint_as_float
 // the product 2^23 * w is exact, so the fused result is the correctly rounded b * w, bit-identical to
 // OpenCV's separately rounded multiply.
 struct ColW {
-    u64 w01[3], c01[3];     // (w, w) and (-2^23 w, -2^23 w) per slot, channels 0 and 1
-    float w2[3], c2[3];     // channel 2
-    __device__ __forceinline__ void set(float a, float b, float c) {
-        const float w[3] = {a, b, c};
+    float w[3], c[3];       // weight and -(2^23 * weight) per slot
+    __device__ __forceinline__ void set(float a, float b, float d) {
+        w[0] = a; w[1] = b; w[2] = d;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const float cc = __fmul_rn(w[k], -8388608.0f);
-            w01[k] = pack2(w[k], w[k]); c01[k] = pack2(cc, cc); w2[k] = w[k]; c2[k] = cc;
-        }
+        for (int k = 0; k < 3; ++k) c[k] = __fmul_rn(w[k], -8388608.0f);
     }
 };
 
-// horizontal pass of one source row for one output column: 9 bytes starting at byte offset a4 + sh/8
-__device__ __forceinline__ void h_area3(const unsigned char* __restrict__ base, int a4, int sh, const ColW& cw, u64& h01, float& h2) {
-    const unsigned q0 = *reinterpret_cast<const unsigned*>(base + a4);
-    const unsigned q1 = *reinterpret_cast<const unsigned*>(base + a4 + 4);
-    const unsigned q2 = *reinterpret_cast<const unsigned*>(base + a4 + 8);
+// shared-memory accesses through 32-bit shared-window addresses (no generic-address arithmetic in the hot loop)
+__device__ __forceinline__ unsigned lds_u32(unsigned addr) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ float lds_f32(unsigned addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ float4 lds_f4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// horizontal pass of one source row for one output column: 9 bytes starting at shared address a4 + sh/8
+__device__ __forceinline__ void h_area3(unsigned a4, int sh, const ColW& cw, u64& h01, float& h2) {
+    const unsigned q0 = lds_u32(a4), q1 = lds_u32(a4 + 4), q2 = lds_u32(a4 + 8);
     const unsigned v0 = __funnelshift_r(q0, q1, sh), v1 = __funnelshift_r(q1, q2, sh), v2 = q2 >> sh;
-    // pixel k = bytes 3k .. 3k+2
-    const u64 p0 = ffma2(pack2(magic_byte<0>(v0), magic_byte<1>(v0)), cw.w01[0], cw.c01[0]);
-    const u64 p1 = ffma2(pack2(magic_byte<3>(v0), magic_byte<0>(v1)), cw.w01[1], cw.c01[1]);
-    const u64 p2 = ffma2(pack2(magic_byte<2>(v1), magic_byte<3>(v1)), cw.w01[2], cw.c01[2]);
-    const float r0 = __fmaf_rn(magic_byte<2>(v0), cw.w2[0], cw.c2[0]);
-    const float r1 = __fmaf_rn(magic_byte<1>(v1), cw.w2[1], cw.c2[1]);
-    const float r2 = __fmaf_rn(magic_byte<0>(v2), cw.w2[2], cw.c2[2]);
+    // pixel k = bytes 3k .. 3k+2; the (w, w) / (c, c) pairs become scalar-broadcast operands of FFMA2
+    const u64 p0 = ffma2(pack2(magic_byte<0>(v0), magic_byte<1>(v0)), pack2(cw.w[0], cw.w[0]), pack2(cw.c[0], cw.c[0]));
+    const u64 p1 = ffma2(pack2(magic_byte<3>(v0), magic_byte<0>(v1)), pack2(cw.w[1], cw.w[1]), pack2(cw.c[1], cw.c[1]));
+    const u64 p2 = ffma2(pack2(magic_byte<2>(v1), magic_byte<3>(v1)), pack2(cw.w[2], cw.w[2]), pack2(cw.c[2], cw.c[2]));
+    const float r0 = __fmaf_rn(magic_byte<2>(v0), cw.w[0], cw.c[0]);
+    const float r1 = __fmaf_rn(magic_byte<1>(v1), cw.w[1], cw.c[1]);
+    const float r2 = __fmaf_rn(magic_byte<0>(v2), cw.w[2], cw.c[2]);
     h01 = fadd2(fadd2(p0, p1), p2);
     h2 = __fadd_rn(__fadd_rn(r0, r1), r2);
 }
 
-// horizontal pass of the fixed-point bilinear: 6 bytes at byte offset a4 + sh/8, result pre-shifted by 4
-__device__ __forceinline__ void h_lin(const unsigned char* __restrict__ base, int a4, int sh, int w0, int w1, int* h) {
-    const unsigned q0 = *reinterpret_cast<const unsigned*>(base + a4);
-    const unsigned q1 = *reinterpret_cast<const unsigned*>(base + a4 + 4);
-    const unsigned q2 = *reinterpret_cast<const unsigned*>(base + a4 + 8);
+// horizontal pass of the fixed-point bilinear: 6 bytes at shared address a4 + sh/8, result pre-shifted by 4
+__device__ __forceinline__ void h_lin(unsigned a4, int sh, int w0, int w1, int* h) {
+    const unsigned q0 = lds_u32(a4), q1 = lds_u32(a4 + 4), q2 = lds_u32(a4 + 8);
     const unsigned v0 = __funnelshift_r(q0, q1, sh), v1 = __funnelshift_r(q1, q2, sh);
     h[0] = (int)((v0 & 0xffu) * w0 + (v0 >> 24) * w1) >> 4;
     h[1] = (int)(((v0 >> 8) & 0xffu) * w0 + (v1 & 0xffu) * w1) >> 4;
@@ -378,7 +379,7 @@ __device__ __forceinline__ int warp_max_i32(int v) {
 
 // TT = compile-time target size (0: run-time T); ALIGNED = the image row pitch W*3 is a multiple of 16 bytes
 template <bool OUT_U8, int TT, bool ALIGNED>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 3)
 bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom,
                      const float4* __restrict__ xdesc, const float4* __restrict__ ydesc, int32_t* __restrict__ wcount,
                      int R, int Trt, int nslot, uchar4 fill, int swap_rb, const float* __restrict__ lut_g,
@@ -388,6 +389,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
     const int T = TT ? TT : Trt;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     unsigned char* wbase = smem + 768 * 4 + wid * WARP_SMEM;          // [2][WARP_BUF] staging, then [2][32] float4 row descriptors
+    const unsigned wbase_s = (unsigned)__cvta_generic_to_shared(wbase), lut_s = (unsigned)__cvta_generic_to_shared(smem);
 
     if (!OUT_U8)
         for (int e = tid; e < 768; e += 256) lut[e] = lut_g[e];
@@ -450,7 +452,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
         const int bh = max(1, min(32, (int)((double)(rows_fit - 3) / (scale_y < 1.0 ? 1.0 : scale_y))));
         const int nb = (new_h + bh - 1) / bh;
         const float4* ydr = ydesc + (size_t)roi * DESC_STRIDE;
-        float* orow = outf + ((size_t)roi * 3 * T + dy0) * T + x;
+        float* optr = outf + ((size_t)roi * 3 * T + dy0) * T + x;     // (plane 0, current row, column x)
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
         // descriptors of batch b (rows b*bh ..) -> ring k, source rows -> buffer k; returns the first source row
@@ -491,30 +493,29 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                 __syncwarp();
                 if (b + 1 < nb) s_lo_next = stage(b + 1, k ^ 1, ydn);
                 ydn = load_desc(b + 2);
-                const unsigned char* cur = wbase + k * WARP_BUF;
-                const float4* ring = reinterpret_cast<const float4*>(wbase + 2 * WARP_BUF + k * WARP_DESC);
+                const unsigned cur = wbase_s + k * WARP_BUF, ring = wbase_s + 2 * WARP_BUF + k * WARP_DESC;
                 const int y0 = b * bh, cnt = min(bh, new_h - y0);
                 if (active) {
                     for (int r = 0; r < cnt; ++r) {
-                        const float4 d = ring[r];
+                        const float4 d = lds_f4(ring + r * 16);
                         const int ysn = __float_as_int(d.w);
                         const int ys = ysn & 0xffffff, n = ysn >> 24;
                         int a = (ys - s_lo_cur) * pitch + colc;
                         if (!ALIGNED) a += (mis0 + ys * misstep) & 15;
-                        if (ys != crow) h_area3(cur, a & ~3, (a & 3) * 8, cw, hc01, hc2);
+                        if (ys != crow) h_area3(cur + (a & ~3), (a & 3) * 8, cw, hc01, hc2);
                         u64 acc01 = fprod2(pack2(d.x, d.x), hc01, nz2);
                         float acc2 = __fmul_rn(d.x, hc2);
                         if (n > 1) {
                             int a1 = a + pitch;
                             if (!ALIGNED) a1 = (ys + 1 - s_lo_cur) * pitch + colc + ((mis0 + (ys + 1) * misstep) & 15);
-                            h_area3(cur, a1 & ~3, (a1 & 3) * 8, cw, hc01, hc2);
+                            h_area3(cur + (a1 & ~3), (a1 & 3) * 8, cw, hc01, hc2);
                             acc01 = fadd2(acc01, fprod2(pack2(d.y, d.y), hc01, nz2));
                             acc2 = __fadd_rn(acc2, __fmul_rn(d.y, hc2));
                         }
                         if (n > 2) {
                             int a2 = a + 2 * pitch;
                             if (!ALIGNED) a2 = (ys + 2 - s_lo_cur) * pitch + colc + ((mis0 + (ys + 2) * misstep) & 15);
-                            h_area3(cur, a2 & ~3, (a2 & 3) * 8, cw, hc01, hc2);
+                            h_area3(cur + (a2 & ~3), (a2 & 3) * 8, cw, hc01, hc2);
                             acc01 = fadd2(acc01, fprod2(pack2(d.z, d.z), hc01, nz2));
                             acc2 = __fadd_rn(acc2, __fmul_rn(d.z, hc2));
                         }
@@ -525,10 +526,10 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                         if (OUT_U8) {
                             out.px(roi, dy0 + y0 + r, x, o0, o1, o2);
                         } else {
-                            float* o = orow + (size_t)(y0 + r) * T;
-                            o[0] = lut[swap ? o2 : o0];
-                            o[plane] = lut[256 + o1];
-                            o[2 * plane] = lut[512 + (swap ? o0 : o2)];
+                            optr[0] = lds_f32(lut_s + 4 * (swap ? o2 : o0));
+                            optr[plane] = lds_f32(lut_s + 1024 + 4 * o1);
+                            optr[2 * plane] = lds_f32(lut_s + 2048 + 4 * (swap ? o0 : o2));
+                            optr += T;
                         }
                     }
                 } else if (padlane) {
@@ -546,19 +547,18 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                 __syncwarp();
                 if (b + 1 < nb) s_lo_next = stage(b + 1, k ^ 1, ydn);
                 ydn = load_desc(b + 2);
-                const unsigned char* cur = wbase + k * WARP_BUF;
-                const float4* ring = reinterpret_cast<const float4*>(wbase + 2 * WARP_BUF + k * WARP_DESC);
+                const unsigned cur = wbase_s + k * WARP_BUF, ring = wbase_s + 2 * WARP_BUF + k * WARP_DESC;
                 const int y0 = b * bh, cnt = min(bh, new_h - y0);
                 if (active) {
                     for (int r = 0; r < cnt; ++r) {
-                        const float4 d = ring[r];
+                        const float4 d = lds_f4(ring + r * 16);
                         const int b0 = __float_as_int(d.x), b1 = __float_as_int(d.y);
                         const int sy0 = __float_as_int(d.w), sy1 = __float_as_int(d.z);
                         if (sy0 != rowA) {
                             if (sy0 == rowB) { HA[0] = HB[0]; HA[1] = HB[1]; HA[2] = HB[2]; }
                             else {
                                 const int a = (sy0 - s_lo_cur) * pitch + colc + (ALIGNED ? 0 : ((mis0 + sy0 * misstep) & 15));
-                                h_lin(cur, a & ~3, (a & 3) * 8, xw0, xw1, HA);
+                                h_lin(cur + (a & ~3), (a & 3) * 8, xw0, xw1, HA);
                             }
                             rowA = sy0;
                         }
@@ -566,7 +566,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                             if (sy1 == rowA) { HB[0] = HA[0]; HB[1] = HA[1]; HB[2] = HA[2]; }
                             else {
                                 const int a = (sy1 - s_lo_cur) * pitch + colc + (ALIGNED ? 0 : ((mis0 + sy1 * misstep) & 15));
-                                h_lin(cur, a & ~3, (a & 3) * 8, xw0, xw1, HB);
+                                h_lin(cur + (a & ~3), (a & 3) * 8, xw0, xw1, HB);
                             }
                             rowB = sy1;
                         }
@@ -576,10 +576,10 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                         if (OUT_U8) {
                             out.px(roi, dy0 + y0 + r, x, o[0], o[1], o[2]);
                         } else {
-                            float* op = orow + (size_t)(y0 + r) * T;
-                            op[0] = lut[swap ? o[2] : o[0]];
-                            op[plane] = lut[256 + o[1]];
-                            op[2 * plane] = lut[512 + (swap ? o[0] : o[2])];
+                            optr[0] = lds_f32(lut_s + 4 * (swap ? o[2] : o[0]));
+                            optr[plane] = lds_f32(lut_s + 1024 + 4 * o[1]);
+                            optr[2 * plane] = lds_f32(lut_s + 2048 + 4 * (swap ? o[0] : o[2]));
+                            optr += T;
                         }
                     }
                 } else if (padlane) {
