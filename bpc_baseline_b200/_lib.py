@@ -25,7 +25,11 @@ SIGNATURES = {
     'bpc_match_workspace_bytes': (_sz, [_i, _i]),
     'bpc_match_triangulate': (_i, [_p, _p, _p, _p, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     'bpc_triangulate': (_i, [_p, _p, _i, _p, _p]),
+    'bpc_projection': (_i, [_p, _p, _i, _p, _p]),
     'bpc_reprojection_error': (_i, [_p, _p, _p, _i, _p, _p]),
+    'bpc_epipolar_error': (_i, [_p, _p, _p, _i, _p, _p]),
+    'bpc_epipolar_error_full': (_i, [_p, _p, _i, _p, _p]),
+    'bpc_triangulate_views': (_i, [_p, _p, _i, _i, _p, _p]),
     'bpc_box_centers': (_i, [_p, _i, _p, _p]),
     'bpc_build_rois': (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     'bpc_roi_crop_workspace_bytes': (_sz, [_i]),

@@ -147,6 +147,54 @@ def reprojection_error(P: torch.Tensor, X: torch.Tensor, pts: torch.Tensor) -> t
     return err
 
 
+def projection(K: torch.Tensor, RT: torch.Tensor) -> torch.Tensor:
+    """P = K (f32 [n,3,3]) @ RT[:3] (f64 [n,4,4]) -> f64 [n,3,4] (process_pose.py:88-92)."""
+    _chk(K, torch.float32, 'K', 3); _chk(RT, torch.float64, 'RT', 3)
+    n = K.shape[0]
+    if tuple(K.shape) != (n, 3, 3) or tuple(RT.shape) != (n, 4, 4):
+        raise RuntimeError('expected K [n,3,3] and RT [n,4,4]')
+    P = torch.empty((n, 3, 4), dtype=torch.float64, device=K.device)
+    with torch.cuda.device(K.device):
+        _lib.check(_lib.load().bpc_projection(_p(K), _p(RT), n, _p(P), _stream(K.device)), 'bpc_projection')
+    return P
+
+
+def epipolar_error(F: torch.Tensor, pt1: torch.Tensor, pt2: torch.Tensor) -> torch.Tensor:
+    """epipolar_error for n (pt1, pt2, F) triples: F f64 [n,3,3], pt f64 [n,2] -> f64 [n] (epipolar_matching.py:5-28)."""
+    _chk(F, torch.float64, 'F', 3); _chk(pt1, torch.float64, 'pt1', 2); _chk(pt2, torch.float64, 'pt2', 2)
+    n = F.shape[0]
+    if tuple(F.shape) != (n, 3, 3) or tuple(pt1.shape) != (n, 2) or tuple(pt2.shape) != (n, 2):
+        raise RuntimeError('expected F [n,3,3], pt1 [n,2], pt2 [n,2]')
+    e = torch.empty((n,), dtype=torch.float64, device=F.device)
+    with torch.cuda.device(F.device):
+        _lib.check(_lib.load().bpc_epipolar_error(_p(F), _p(pt1), _p(pt2), n, _p(e), _stream(F.device)), 'bpc_epipolar_error')
+    return e
+
+
+def epipolar_error_full(F: torch.Tensor, pts: torch.Tensor) -> torch.Tensor:
+    """(e12 + e13 + e23) / 3 for n triples: F f64 [n,3,3,3], pts f64 [n,3,2] -> f64 [n] (epipolar_matching.py:73-81)."""
+    _chk(F, torch.float64, 'F', 4); _chk(pts, torch.float64, 'pts', 3)
+    n = F.shape[0]
+    if tuple(F.shape) != (n, 3, 3, 3) or tuple(pts.shape) != (n, 3, 2):
+        raise RuntimeError('expected F [n,3,3,3] and pts [n,3,2]')
+    e = torch.empty((n,), dtype=torch.float64, device=F.device)
+    with torch.cuda.device(F.device):
+        _lib.check(_lib.load().bpc_epipolar_error_full(_p(F), _p(pts), n, _p(e), _stream(F.device)), 'bpc_epipolar_error_full')
+    return e
+
+
+def triangulate_views(P: torch.Tensor, pts: torch.Tensor) -> torch.Tensor:
+    """DLT with V views (2..8): P f64 [n,V,3,4], pts f64 [n,V,2] -> X f64 [n,3] (epipolar_matching.py:118-127)."""
+    _chk(P, torch.float64, 'P', 4); _chk(pts, torch.float64, 'pts', 3)
+    n, V = P.shape[0], P.shape[1]
+    if tuple(P.shape) != (n, V, 3, 4) or tuple(pts.shape) != (n, V, 2) or not 2 <= V <= 8:
+        raise RuntimeError('expected P [n,V,3,4] and pts [n,V,2] with 2 <= V <= 8')
+    X = torch.empty((n, 3), dtype=torch.float64, device=P.device)
+    with torch.cuda.device(P.device):
+        _lib.check(_lib.load().bpc_triangulate_views(_p(P), _p(pts), n, V, _p(X), _stream(P.device)), 'bpc_triangulate_views')
+    return X
+
+
 def build_rois(boxes: torch.Tensor, idx: torch.Tensor, n: torch.Tensor, image_of_scene: torch.Tensor,
                rois: Optional[torch.Tensor] = None) -> tuple[torch.Tensor, torch.Tensor]:
     """(rois i32 [S*Kmax*3, 5], scene_offset i32 [S+1]); 3 ROIs per match in (scene, match, view) order.

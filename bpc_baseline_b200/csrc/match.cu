@@ -416,6 +416,15 @@ __global__ void bpc_cost_tensor_kernel(const double* __restrict__ F, const doubl
     }
 }
 
+// P = K (float32) @ RT[:3] (float64) for n cameras (process_pose.py:91)
+__global__ void bpc_projection_kernel(const float* __restrict__ K, const double* __restrict__ RT, int n, double* __restrict__ P) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double pm[12];
+    projection(K + (size_t)t * 9, RT + (size_t)t * 16, pm);
+    for (int e = 0; e < 12; ++e) P[(size_t)t * 12 + e] = pm[e];
+}
+
 __global__ void bpc_triangulate_kernel(const double* __restrict__ P, const double* __restrict__ pts, int n, double* __restrict__ X) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -424,6 +433,85 @@ __global__ void bpc_triangulate_kernel(const double* __restrict__ P, const doubl
     for (int e = 0; e < 6; ++e) xy[e] = pts[(size_t)t * 6 + e];
     triangulate3(Pm, xy, x);
     X[(size_t)t * 3 + 0] = x[0]; X[(size_t)t * 3 + 1] = x[1]; X[(size_t)t * 3 + 2] = x[2];
+}
+
+// epipolar_error(pt1, pt2, F) for n independent (pt1, pt2, F) triples (epipolar_matching.py:5-28)
+__global__ void bpc_epipolar_error_kernel(const double* __restrict__ F, const double* __restrict__ p1, const double* __restrict__ p2,
+                                          int n, double* __restrict__ e) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double f[9], l1[3], l2[3];
+    for (int k = 0; k < 9; ++k) f[k] = F[(size_t)t * 9 + k];
+    const double x1 = p1[(size_t)t * 2], y1 = p1[(size_t)t * 2 + 1], x2 = p2[(size_t)t * 2], y2 = p2[(size_t)t * 2 + 1];
+    const bool ok2 = epiline(f, 0, x1, y1, l2);       // l2 = F @ pt1: line in the second camera
+    const bool ok1 = epiline(f, 1, x2, y2, l1);       // l1 = F.T @ pt2
+    const double d1 = ok1 ? line_point(l1, x1, y1) : 9999.0;
+    const double d2 = ok2 ? line_point(l2, x2, y2) : 9999.0;
+    e[t] = dmul(0.5, dadd(d1, d2));
+}
+
+// epipolar_error_full(pt1, pt2, pt3, F12, F13, F23) for n triples (epipolar_matching.py:73-81); F = [n][3][9]
+__global__ void bpc_epipolar_error_full_kernel(const double* __restrict__ F, const double* __restrict__ pts, int n, double* __restrict__ e) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const double* p = pts + (size_t)t * 6;
+    double acc[3];
+    const int ia[3] = {0, 0, 1}, ib[3] = {1, 2, 2};
+    for (int pr = 0; pr < 3; ++pr) {
+        double f[9], l1[3], l2[3];
+        for (int k = 0; k < 9; ++k) f[k] = F[((size_t)t * 3 + pr) * 9 + k];
+        const double xa = p[ia[pr] * 2], ya = p[ia[pr] * 2 + 1], xb = p[ib[pr] * 2], yb = p[ib[pr] * 2 + 1];
+        const bool ok2 = epiline(f, 0, xa, ya, l2);
+        const bool ok1 = epiline(f, 1, xb, yb, l1);
+        const double d1 = ok1 ? line_point(l1, xa, ya) : 9999.0;
+        const double d2 = ok2 ? line_point(l2, xb, yb) : 9999.0;
+        acc[pr] = dmul(0.5, dadd(d1, d2));
+    }
+    e[t] = ddiv(dadd(dadd(acc[0], acc[1]), acc[2]), 3.0);
+}
+
+// DLT for V views (2 <= V <= 8), one thread per point; same one-sided Jacobi as triangulate3 on a (2V x 4) matrix
+__global__ void bpc_triangulate_views_kernel(const double* __restrict__ P, const double* __restrict__ pts, int n, int V, double* __restrict__ X) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double A[16][4], Vm[4][4];
+    const int rows = 2 * V;
+    for (int v = 0; v < V; ++v) {
+        const double* Pm = P + ((size_t)t * V + v) * 12;
+        const double x = pts[((size_t)t * V + v) * 2], y = pts[((size_t)t * V + v) * 2 + 1];
+        for (int c = 0; c < 4; ++c) {
+            A[2 * v][c] = dsub(dmul(x, Pm[8 + c]), Pm[c]);
+            A[2 * v + 1][c] = dsub(dmul(y, Pm[8 + c]), Pm[4 + c]);
+        }
+    }
+    for (int r = 0; r < 4; ++r)
+        for (int c = 0; c < 4; ++c) Vm[r][c] = (r == c) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 20; ++sweep) {
+        bool rotated = false;
+        for (int p = 0; p < 3; ++p)
+            for (int q = p + 1; q < 4; ++q) {
+                double alpha = 0.0, beta = 0.0, gamma = 0.0;
+                for (int r = 0; r < rows; ++r) { alpha += A[r][p] * A[r][p]; beta += A[r][q] * A[r][q]; gamma += A[r][p] * A[r][q]; }
+                if (fabs(gamma) > 1e-15 * sqrt(alpha * beta) && fabs(gamma) > 1e-300) {
+                    const double zeta = (beta - alpha) / (2.0 * gamma);
+                    const double tt = fabs(zeta) > 1e150 ? 0.5 / zeta : copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    const double cs = 1.0 / sqrt(1.0 + tt * tt), sn = cs * tt;
+                    for (int r = 0; r < rows; ++r) { const double ap = A[r][p], aq = A[r][q]; A[r][p] = cs * ap - sn * aq; A[r][q] = sn * ap + cs * aq; }
+                    for (int r = 0; r < 4; ++r) { const double vp = Vm[r][p], vq = Vm[r][q]; Vm[r][p] = cs * vp - sn * vq; Vm[r][q] = sn * vp + cs * vq; }
+                    rotated = true;
+                }
+            }
+        if (!rotated) break;
+    }
+    double best = 0.0; int bi = 0;
+    for (int c = 0; c < 4; ++c) {
+        double nrm = 0.0;
+        for (int r = 0; r < rows; ++r) nrm += A[r][c] * A[r][c];
+        if (c == 0 || nrm < best) { best = nrm; bi = c; }
+    }
+    X[(size_t)t * 3 + 0] = Vm[0][bi] / Vm[3][bi];
+    X[(size_t)t * 3 + 1] = Vm[1][bi] / Vm[3][bi];
+    X[(size_t)t * 3 + 2] = Vm[2][bi] / Vm[3][bi];
 }
 
 __global__ void bpc_reproj_kernel(const double* __restrict__ P, const double* __restrict__ X, const double* __restrict__ pts,
@@ -555,6 +643,14 @@ extern "C" int bpc_match_triangulate(const float* Ks, const double* RTs, const d
     return BPC_OK;
 }
 
+extern "C" int bpc_projection(const float* K, const double* RT, int n, double* P, void* stream) {
+    if (n < 0 || (n > 0 && (!K || !RT || !P))) return BPC_EINVAL;
+    if (n == 0) return BPC_OK;
+    bpc_projection_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(K, RT, n, P);
+    BPC_LAUNCH_CHECK();
+    return BPC_OK;
+}
+
 extern "C" int bpc_triangulate(const double* P, const double* pts, int n, double* X, void* stream) {
     if (n < 0 || (n > 0 && (!P || !pts || !X))) return BPC_EINVAL;
     if (n == 0) return BPC_OK;
@@ -567,6 +663,30 @@ extern "C" int bpc_reprojection_error(const double* P, const double* X, const do
     if (n < 0 || (n > 0 && (!P || !pts || !X || !err))) return BPC_EINVAL;
     if (n == 0) return BPC_OK;
     bpc_reproj_kernel<<<(n * 3 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P, X, pts, n, err);
+    BPC_LAUNCH_CHECK();
+    return BPC_OK;
+}
+
+extern "C" int bpc_epipolar_error(const double* F, const double* pt1, const double* pt2, int n, double* e, void* stream) {
+    if (n < 0 || (n > 0 && (!F || !pt1 || !pt2 || !e))) return BPC_EINVAL;
+    if (n == 0) return BPC_OK;
+    bpc_epipolar_error_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(F, pt1, pt2, n, e);
+    BPC_LAUNCH_CHECK();
+    return BPC_OK;
+}
+
+extern "C" int bpc_epipolar_error_full(const double* F, const double* pts, int n, double* e, void* stream) {
+    if (n < 0 || (n > 0 && (!F || !pts || !e))) return BPC_EINVAL;
+    if (n == 0) return BPC_OK;
+    bpc_epipolar_error_full_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(F, pts, n, e);
+    BPC_LAUNCH_CHECK();
+    return BPC_OK;
+}
+
+extern "C" int bpc_triangulate_views(const double* P, const double* pts, int n, int V, double* X, void* stream) {
+    if (n < 0 || V < 2 || V > 8 || (n > 0 && (!P || !pts || !X))) return BPC_EINVAL;
+    if (n == 0) return BPC_OK;
+    bpc_triangulate_views_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(P, pts, n, V, X);
     BPC_LAUNCH_CHECK();
     return BPC_OK;
 }

@@ -114,7 +114,23 @@ int bpc_match_triangulate(const float* Ks, const double* RTs, const double* cent
  *   err  double [n][3]
  */
 int bpc_triangulate(const double* P, const double* pts, int n, double* X, void* stream);
+/* a7. Projection matrices P = K (float32) @ RT[:3] (float64), bpc/inference/process_pose.py:88-92.
+ *   K float [n][3][3], RT double [n][4][4]  ->  P double [n][3][4] */
+int bpc_projection(const float* K, const double* RT, int n, double* P, void* stream);
 int bpc_reprojection_error(const double* P, const double* X, const double* pts, int n, double* err, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a2, a3. Scalar distances for n independent inputs (the reference's per-pair functions).
+ * bpc_epipolar_error      replaces epipolar_error(pt1, pt2, F), epipolar_matching.py:5-28
+ *   F double [n][3][3], pt1 / pt2 double [n][2]  ->  e double [n]
+ * bpc_epipolar_error_full replaces epipolar_error_full(pt1, pt2, pt3, F12, F13, F23), :73-81
+ *   F double [n][3][3][3] (12, 13, 23), pts double [n][3][2]  ->  e double [n]
+ * bpc_triangulate_views   triangulate_multi_view for V views (2 <= V <= 8), :118-127
+ *   P double [n][V][3][4], pts double [n][V][2]  ->  X double [n][3]
+ */
+int bpc_epipolar_error(const double* F, const double* pt1, const double* pt2, int n, double* e, void* stream);
+int bpc_epipolar_error_full(const double* F, const double* pts, int n, double* e, void* stream);
+int bpc_triangulate_views(const double* P, const double* pts, int n, int V, double* X, void* stream);
 
 /* Centres from integer boxes: cx = 0.5*(x1+x2), cy = 0.5*(y1+y2), process_pose.py:134-136. */
 int bpc_box_centers(const int32_t* boxes, int count, double* centers, void* stream);

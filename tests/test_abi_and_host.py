@@ -1,0 +1,124 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/bpc_b200.h declares, argument
+validation that needs no GPU, and the host-side logic (scene generator, ROI mirror, install() rebinding)."""
+import ctypes
+import os
+import re
+import types
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from bpc_baseline_b200 import _lib, build
+    build.build()                                        # nvcc cross-compiles for sm_100a without a GPU
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from bpc_baseline_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'bpc_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(bpc_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in bpc_b200.h but not exported'
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.bpc_abi_version() == 1
+
+
+def test_error_strings_and_argument_validation(lib):
+    assert lib.bpc_error_string(0) == b'ok'
+    assert b'invalid argument' in lib.bpc_error_string(-1)
+    # argument errors are detected before any CUDA call, so they can be exercised without a GPU
+    assert lib.bpc_fundamental(None, None, -1, None, None) == -1
+    assert lib.bpc_fundamental(None, None, 4, None, None) == -1
+    assert lib.bpc_fundamental(None, None, 0, None, None) == 0
+    assert lib.bpc_match_triangulate(None, None, None, None, 0, 0, 30.0, None, None, None, None, None, None, None, 0, None) == -1
+    assert lib.bpc_match_triangulate(None, None, None, None, 0, 20, 30.0, None, None, None, None, None, None, None, 0, None) == 0
+    fill = (ctypes.c_uint8 * 3)(255, 255, 255)
+    assert lib.bpc_roi_crop(None, 1, 8, 8, None, 0, None, 0, 300, fill, 1, None, None, None, None, 0, None) == -1   # T > 256
+    assert lib.bpc_roi_crop(None, 1, 8, 8, None, 0, None, 0, 224, fill, 1, None, None, None, None, 0, None) == 0    # R == 0
+    assert lib.bpc_roi_crop_workspace_bytes(8192) > 8192 * 8192
+    assert lib.bpc_triangulate_views(None, None, 1, 9, None, None) == -1
+    assert lib.bpc_launch_count() == 0
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from bpc_baseline_b200 import _lib
+    monkeypatch.setattr(_lib, '_lib', None)
+    monkeypatch.setattr(_lib, 'LIB_PATH', str(tmp_path / 'nope.so'))
+    with pytest.raises(_lib.BpcError, match='no CPU fallback'):
+        _lib.load()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'bpc_baseline_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
+
+
+def test_batched_api_rejects_cpu_tensors():
+    import torch
+    from bpc_baseline_b200 import batched
+    with pytest.raises(RuntimeError, match='CUDA tensor'):
+        batched.fundamental(torch.zeros(1, 3, 3, 3), torch.zeros(1, 3, 4, 4, dtype=torch.float64))
+    with pytest.raises(RuntimeError, match='CUDA tensor'):
+        batched.roi_crop(torch.zeros(1, 8, 8, 3, dtype=torch.uint8), torch.zeros(1, 5, dtype=torch.int32))
+
+
+def test_scene_generator_is_chunk_reproducible_and_valid():
+    from bpc_baseline_b200 import synth
+    a = synth.make_scenes(600, 7, p_drop=0.2, n_dup=1, n_false=1)
+    b = synth.make_scenes(88, 7, first=512, p_drop=0.2, n_dup=1, n_false=1)
+    for k in ('Ks', 'RTs', 'boxes', 'centers', 'counts'):
+        assert np.array_equal(getattr(a, k)[512:600], getattr(b, k))
+    assert a.Ks.dtype == np.float32 and a.RTs.dtype == np.float64 and a.boxes.dtype == np.int32
+    # RT carries float32-rounded values (data_utils.py:383-387); rotations are orthonormal to float32 accuracy
+    assert np.array_equal(a.RTs, a.RTs.astype(np.float32).astype(np.float64))
+    R = a.RTs[:, :, :3, :3]
+    np.testing.assert_allclose(R @ R.transpose(0, 1, 3, 2), np.broadcast_to(np.eye(3), R.shape), atol=1e-6)
+    for s in range(0, 600, 97):
+        for c in range(3):
+            n = a.counts[s, c]
+            bx = a.boxes[s, c, :n]
+            assert np.all(bx[:, 0] >= 0) and np.all(bx[:, 1] >= 0) and np.all(bx[:, 2] <= synth.IMG_W) and np.all(bx[:, 3] <= synth.IMG_H)
+            assert np.all(bx[:, 2] - bx[:, 0] >= 8) and np.all(bx[:, 3] - bx[:, 1] >= 8)
+            assert np.array_equal(a.centers[s, c, :n, 0], 0.5 * (bx[:, 0] + bx[:, 2]))
+
+
+def test_rois_host_mirror_and_algorithmic_bytes():
+    from bpc_baseline_b200 import pipeline, synth
+    boxes = np.zeros((2, 3, 4, 4), np.int32)
+    boxes[..., 2] = 100; boxes[..., 3] = 50
+    boxes[1, 2, 3] = (5, 6, 25, 36)
+    idx = np.full((2, 4, 3), -1, np.int32)
+    idx[0, 0] = (0, 1, 2); idx[1, 0] = (1, 1, 3); idx[1, 1] = (0, 0, 0)
+    rois = synth.rois_for_matches(boxes, idx, np.array([1, 2]), np.arange(6, dtype=np.int32).reshape(2, 3))
+    assert rois.shape == (9, 5) and list(rois[5]) == [5, 5, 6, 25, 36] and list(rois[:, 0]) == [0, 1, 2, 3, 4, 5, 3, 4, 5]
+    want = 8 * (3 * 100 * 50) + 3 * 20 * 30 + 9 * (3 * 224 * 224 * 4 + 20)
+    assert pipeline.algorithmic_crop_bytes(rois, 224) == want
+
+
+def test_install_only_touches_imported_modules(lib):
+    import sys
+    import bpc_baseline_b200 as pkg
+    mod = types.ModuleType('fakeref.inference.epipolar_matching')
+    sentinel = object()
+    mod.match_objects = sentinel
+    sys.modules['fakeref.inference.epipolar_matching'] = mod
+    try:
+        done = pkg.install('fakeref')
+        assert done == ['fakeref.inference.epipolar_matching.match_objects']
+        assert mod.match_objects is not sentinel
+        pkg.uninstall()
+        assert mod.match_objects is sentinel
+    finally:
+        pkg.uninstall()
+        sys.modules.pop('fakeref.inference.epipolar_matching', None)
