@@ -235,7 +235,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from bpc_baseline_b200 import _lib, batched, pipeline, synth
+    from bpc_baseline_b200 import _lib, batched, distributed, pipeline, synth
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -275,10 +275,6 @@ def main():
     n_rois_arg = 0 if args.no_crops else n_rois
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
-    gathered = None
-    if world > 1:
-        rec = torch.empty((S, Dmax, 8), dtype=torch.float64, device=dev)
-        gathered = torch.empty((world, S, Dmax, 8), dtype=torch.float64, device=dev)
 
     def step(k=None):
         e = ev[k] if k is not None else None
@@ -287,11 +283,7 @@ def main():
         r, _ = pipe.run_device(Ks, RTs, centers, counts, boxes, images, ios_d, n_rois_host=n_rois_arg,
                                events=(e[0], e[1], e[2]) if e is not None else None)
         if world > 1:                     # final gather of the pose records over NVLink
-            rec[..., 0:3] = r.idx.to(torch.float64)
-            rec[..., 3] = r.cost.to(torch.float64)
-            rec[..., 4:7] = r.X
-            rec[..., 7] = r.n.to(torch.float64)[:, None]
-            dist.all_gather_into_tensor(gathered, rec)
+            distributed.gather_records(distributed.pack_records(r.idx, r.n, r.cost, r.X))
 
     for _ in range(max(args.warmup, 3)):
         step()
