@@ -848,7 +848,12 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
         if (e != cudaSuccess) return (int)e;
         const long long nitems = (long long)R * nslot;
         const long long want = (nitems + WARPK_WARPS - 1) / WARPK_WARPS;
-        const int grid = (int)(want < 148 * 4 ? want : 148 * 4);
+        int dev = 0, sms = 148, per_sm = 3;                     // persistent grid: every resident CTA slot, no more
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, WARPK_SMEM) != cudaSuccess || per_sm < 1) per_sm = 1;
+        const long long slots = (long long)sms * per_sm;
+        const int grid = (int)(want < slots ? want : slots);
         fn<<<grid, 256, WARPK_SMEM, st>>>(images, B, H, W, geom, xdesc, ydesc, wcount, R, T, nslot, f4, swap_rb, lut, outf, outb);
         BPC_LAUNCH_CHECK();
     }
