@@ -32,7 +32,7 @@ constexpr int CROP_BAND = 8;                 // generic kernel: output rows per 
 constexpr int CROP_RAW_BYTES = 40 * 1024;    // generic kernel: staged source bytes
 constexpr int WARP_BUF = 2560;               // warp kernel: bytes of one staging buffer (two per warp)
 constexpr int WARP_DESC = 32 * 16;           // warp kernel: 32 row descriptors (two rings per warp)
-constexpr int WARP_SMEM = 2 * WARP_BUF + 2 * WARP_DESC;
+constexpr int WARP_SMEM = 2 * WARP_BUF + 2 * WARP_DESC + 16;   // + two mbarriers
 constexpr int WARPK_WARPS = 8;
 constexpr int WARPK_SMEM = WARPK_WARPS * WARP_SMEM + 768 * 4;
 constexpr int DESC_STRIDE = 256;             // descriptors per ROI and axis (T <= 256)
@@ -310,7 +310,10 @@ struct ColW {
     __device__ __forceinline__ void set(float a, float b, float d) {
         w[0] = a; w[1] = b; w[2] = d;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) c[k] = __fmul_rn(w[k], -8388608.0f);
+        for (int k = 0; k < 3; ++k) {
+            c[k] = __fmul_rn(w[k], -8388608.0f);
+            asm volatile("" : "+f"(c[k]));      // opaque: keep it in a register instead of re-multiplying in the inner loop
+        }
     }
 };
 
@@ -348,14 +351,55 @@ __device__ __forceinline__ void h_lin(unsigned a4, int sh, int w0, int w1, int* 
 }
 
 // cvRound(v) for 0 <= v < 2^22 without F2I: adding 2^23 leaves round-half-even(v) in the low mantissa bits
-__device__ __forceinline__ int round_u8(float v) { return min(255, __float_as_int(__fadd_rn(v, 8388608.0f)) & 0x1ff); }
+// (no clamp: the tap weights of each axis sum to 1 within a few ulp, so v <= 255.001 and the result is <= 255)
+__device__ __forceinline__ int round_u8(float v) { return __float_as_int(__fadd_rn(v, 8388608.0f)) & 0xff; }
 
-// 16-byte cp.async of rows [s_lo, s_lo + count) of a strip; lane (lr, lv) copies vector lv of rows lr, lr + rpp, ...
-__device__ __forceinline__ void warp_stage(unsigned char* buf, unsigned long long src_seg, unsigned long long rowstride,
-                                           unsigned long long img_end, int s_lo, int count, int pitch, int lr, int lv, int rpp) {
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier in shared memory ----
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, unsigned long long src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "BPC_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra BPC_DONE;\n"
+                 "bra BPC_WAIT;\n"
+                 "BPC_DONE:\n"
+                 "}" :: "r"(bar), "r"(parity) : "memory");
+}
+
+// Stage rows [s_lo, s_lo + count) of a strip into a warp buffer.  Normal case: one TMA bulk copy of `pitch` bytes
+// per row (lane r issues row r), completion counted in bytes on the warp's mbarrier -> returns 1.  If the
+// 16-byte-aligned over-read of the last row would leave the image pool (last rows of the last image) the
+// rows are copied with guarded 16-byte cp.async instead -> returns 0 (wait with cp.async.wait_group).
+__device__ __forceinline__ int warp_stage(unsigned char* buf, unsigned buf_s, unsigned bar_s, unsigned long long src_seg,
+                                          unsigned long long rowstride, unsigned long long img_end, int s_lo, int count,
+                                          int pitch, int lane, int lr, int lv, int rpp) {
+    const unsigned long long first = src_seg + (unsigned long long)s_lo * rowstride;
+    const unsigned long long last_end = ((first + (unsigned long long)(count - 1) * rowstride) & ~15ull) + (unsigned long long)pitch;
+    if (last_end <= img_end) {
+        if (lane == 0) mbar_expect_tx(bar_s, (unsigned)(count * pitch));
+        __syncwarp();
+        unsigned long long ga = first + (unsigned long long)lane * rowstride;
+        unsigned dst = buf_s + lane * pitch;
+        for (int r = lane; r < count; r += 32) {
+            bulk_g2s(dst, ga & ~15ull, (unsigned)pitch, bar_s);
+            ga += 32ull * rowstride;
+            dst += 32 * pitch;
+        }
+        return 1;
+    }
     if (lr < rpp) {
         for (int r = lr; r < count; r += rpp) {
-            const unsigned long long ga = src_seg + (unsigned long long)(s_lo + r) * rowstride;
+            const unsigned long long ga = first + (unsigned long long)r * rowstride;
             const unsigned long long a = (ga & ~15ull) + (unsigned long long)lv * 16ull;
             unsigned char* dst = buf + r * pitch + lv * 16;
             if (a + 16ull <= img_end) {
@@ -369,6 +413,7 @@ __device__ __forceinline__ void warp_stage(unsigned char* buf, unsigned long lon
         }
     }
     cp_async_commit();
+    return 0;
 }
 
 __device__ __forceinline__ int warp_max_i32(int v) {
@@ -378,7 +423,8 @@ __device__ __forceinline__ int warp_max_i32(int v) {
 }
 
 // TT = compile-time target size (0: run-time T); ALIGNED = the image row pitch W*3 is a multiple of 16 bytes
-template <bool OUT_U8, int TT, bool ALIGNED>
+// SWAP = write the planes in R, G, B order from B, G, R sources (cv2.COLOR_BGR2RGB, process_pose.py:206)
+template <bool OUT_U8, int TT, bool ALIGNED, bool SWAP>
 __global__ void __launch_bounds__(256, 3)
 bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom,
                      const float4* __restrict__ xdesc, const float4* __restrict__ ydesc, int32_t* __restrict__ wcount,
@@ -391,12 +437,15 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
     unsigned char* wbase = smem + 768 * 4 + wid * WARP_SMEM;          // [2][WARP_BUF] staging, then [2][32] float4 row descriptors
     const unsigned wbase_s = (unsigned)__cvta_generic_to_shared(wbase), lut_s = (unsigned)__cvta_generic_to_shared(smem);
 
+    const unsigned bar_s = wbase_s + 2 * WARP_BUF + 2 * WARP_DESC;     // two mbarriers, one per staging buffer
+    if (lane == 0) { mbar_init(bar_s, 1); mbar_init(bar_s + 8, 1); }
+    unsigned phase0 = 0, phase1 = 0;                                      // parity of the next completion of each barrier
     if (!OUT_U8)
         for (int e = tid; e < 768; e += 256) lut[e] = lut_g[e];
     __syncthreads();
     Out<OUT_U8> out;
     out_init(out, outf, outb, lut, T, swap_rb, fill);
-    const bool swap = swap_rb != 0;
+    constexpr bool swap = SWAP;
     const size_t plane = (size_t)T * T;
     const unsigned long long rowstride = (unsigned long long)W * 3ull;
     const unsigned long long img_end = (unsigned long long)(uintptr_t)images + (unsigned long long)B * H * rowstride;
@@ -447,6 +496,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
         const unsigned long long src_seg = gp->src + 3ull * (unsigned long long)xs_min;
         const int mis0 = (int)(src_seg & 15ull), misstep = ALIGNED ? 0 : (int)(rowstride & 15ull);
         const int colc = 3 * (xs - xs_min) + (ALIGNED ? mis0 : 0);
+        const int colc4 = colc & ~3, shc = (colc & 3) * 8;
         const int rows_fit = WARP_BUF / pitch;
         const double scale_y = gp->scale_y;
         const int bh = max(1, min(32, (int)((double)(rows_fit - 3) / (scale_y < 1.0 ? 1.0 : scale_y))));
@@ -456,6 +506,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
         // descriptors of batch b (rows b*bh ..) -> ring k, source rows -> buffer k; returns the first source row
+        int bulk_cur = 0, bulk_next = 0;
         auto stage = [&](int b, int k, const float4& yd) -> int {
             const int cnt = min(bh, new_h - b * bh);
             if (lane < cnt) reinterpret_cast<float4*>(wbase + 2 * WARP_BUF + k * WARP_DESC)[lane] = yd;
@@ -468,7 +519,8 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             }
             const int s_lo = __shfl_sync(0xffffffffu, lo, 0);
             const int s_hi = __shfl_sync(0xffffffffu, hi, cnt - 1);
-            warp_stage(wbase + k * WARP_BUF, src_seg, rowstride, img_end, s_lo, s_hi - s_lo + 1, pitch, lr, lv, rpp);
+            bulk_next = warp_stage(wbase + k * WARP_BUF, wbase_s + k * WARP_BUF, bar_s + 8 * k, src_seg, rowstride, img_end, s_lo,
+                                   s_hi - s_lo + 1, pitch, lane, lr, lv, rpp);
             return s_lo;
         };
         auto load_desc = [&](int b) -> float4 {
@@ -478,6 +530,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
 
         __syncwarp();                                   // previous item finished with the buffers
         int s_lo_cur = stage(0, 0, load_desc(0));
+        bulk_cur = bulk_next;
         float4 ydn = load_desc(1);
         int s_lo_next = 0;
 
@@ -489,7 +542,11 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             float hc2 = 0.f;
             for (int b = 0; b < nb; ++b) {
                 const int k = b & 1;
-                cp_async_wait_all();
+                if (bulk_cur) {
+                    if (k == 0) { mbar_wait(bar_s, phase0); phase0 ^= 1u; } else { mbar_wait(bar_s + 8, phase1); phase1 ^= 1u; }
+                } else {
+                    cp_async_wait_all();
+                }
                 __syncwarp();
                 if (b + 1 < nb) s_lo_next = stage(b + 1, k ^ 1, ydn);
                 ydn = load_desc(b + 2);
@@ -500,22 +557,25 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                         const float4 d = lds_f4(ring + r * 16);
                         const int ysn = __float_as_int(d.w);
                         const int ys = ysn & 0xffffff, n = ysn >> 24;
+                        // byte address of the lane's first tap in row ys; with a 16-byte-multiple image pitch the
+                        // word offset and the funnel shift are per-item constants (pitch is a multiple of 16)
                         int a = (ys - s_lo_cur) * pitch + colc;
                         if (!ALIGNED) a += (mis0 + ys * misstep) & 15;
-                        if (ys != crow) h_area3(cur + (a & ~3), (a & 3) * 8, cw, hc01, hc2);
+                        const unsigned a4 = ALIGNED ? cur + (ys - s_lo_cur) * pitch + colc4 : cur + (a & ~3);
+                        if (ys != crow) h_area3(a4, ALIGNED ? shc : (a & 3) * 8, cw, hc01, hc2);
                         u64 acc01 = fprod2(pack2(d.x, d.x), hc01, nz2);
                         float acc2 = __fmul_rn(d.x, hc2);
                         if (n > 1) {
                             int a1 = a + pitch;
                             if (!ALIGNED) a1 = (ys + 1 - s_lo_cur) * pitch + colc + ((mis0 + (ys + 1) * misstep) & 15);
-                            h_area3(cur + (a1 & ~3), (a1 & 3) * 8, cw, hc01, hc2);
+                            h_area3(ALIGNED ? a4 + pitch : cur + (a1 & ~3), ALIGNED ? shc : (a1 & 3) * 8, cw, hc01, hc2);
                             acc01 = fadd2(acc01, fprod2(pack2(d.y, d.y), hc01, nz2));
                             acc2 = __fadd_rn(acc2, __fmul_rn(d.y, hc2));
                         }
                         if (n > 2) {
                             int a2 = a + 2 * pitch;
                             if (!ALIGNED) a2 = (ys + 2 - s_lo_cur) * pitch + colc + ((mis0 + (ys + 2) * misstep) & 15);
-                            h_area3(cur + (a2 & ~3), (a2 & 3) * 8, cw, hc01, hc2);
+                            h_area3(ALIGNED ? a4 + 2 * pitch : cur + (a2 & ~3), ALIGNED ? shc : (a2 & 3) * 8, cw, hc01, hc2);
                             acc01 = fadd2(acc01, fprod2(pack2(d.z, d.z), hc01, nz2));
                             acc2 = __fadd_rn(acc2, __fmul_rn(d.z, hc2));
                         }
@@ -536,6 +596,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                     for (int r = 0; r < cnt; ++r) out.pad(roi, dy0 + y0 + r, x);
                 }
                 s_lo_cur = s_lo_next;
+                bulk_cur = bulk_next;
             }
         } else {
             const int xw0 = __float_as_int(xd.x), xw1 = __float_as_int(xd.y);
@@ -543,7 +604,11 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             int HA[3] = {0, 0, 0}, HB[3] = {0, 0, 0};
             for (int b = 0; b < nb; ++b) {
                 const int k = b & 1;
-                cp_async_wait_all();
+                if (bulk_cur) {
+                    if (k == 0) { mbar_wait(bar_s, phase0); phase0 ^= 1u; } else { mbar_wait(bar_s + 8, phase1); phase1 ^= 1u; }
+                } else {
+                    cp_async_wait_all();
+                }
                 __syncwarp();
                 if (b + 1 < nb) s_lo_next = stage(b + 1, k ^ 1, ydn);
                 ydn = load_desc(b + 2);
@@ -586,6 +651,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                     for (int r = 0; r < cnt; ++r) out.pad(roi, dy0 + y0 + r, x);
                 }
                 s_lo_cur = s_lo_next;
+                bulk_cur = bulk_next;
             }
         }
     }
@@ -840,10 +906,15 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
                                uchar4, int, const float*, float*, uint8_t*);
         const bool aligned = ((long long)W * 3) % 16 == 0;
         WarpFn fn;
-        if (OUT_U8) fn = aligned ? bpc_crop_warp_kernel<OUT_U8, 0, true> : bpc_crop_warp_kernel<OUT_U8, 0, false>;
-        else if (T == 224) fn = aligned ? bpc_crop_warp_kernel<OUT_U8, 224, true> : bpc_crop_warp_kernel<OUT_U8, 224, false>;
-        else if (T == 256) fn = aligned ? bpc_crop_warp_kernel<OUT_U8, 256, true> : bpc_crop_warp_kernel<OUT_U8, 256, false>;
-        else fn = aligned ? bpc_crop_warp_kernel<OUT_U8, 0, true> : bpc_crop_warp_kernel<OUT_U8, 0, false>;
+        const bool sw = swap_rb != 0;
+#define BPC_PICK(TTV)                                                                                                  \
+    (aligned ? (sw ? bpc_crop_warp_kernel<OUT_U8, TTV, true, true> : bpc_crop_warp_kernel<OUT_U8, TTV, true, false>)   \
+             : (sw ? bpc_crop_warp_kernel<OUT_U8, TTV, false, true> : bpc_crop_warp_kernel<OUT_U8, TTV, false, false>))
+        if (OUT_U8) fn = aligned ? bpc_crop_warp_kernel<OUT_U8, 0, true, false> : bpc_crop_warp_kernel<OUT_U8, 0, false, false>;
+        else if (T == 224) fn = BPC_PICK(224);
+        else if (T == 256) fn = BPC_PICK(256);
+        else fn = BPC_PICK(0);
+#undef BPC_PICK
         e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, WARPK_SMEM);
         if (e != cudaSuccess) return (int)e;
         const long long nitems = (long long)R * nslot;

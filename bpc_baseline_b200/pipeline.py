@@ -110,6 +110,74 @@ class MatchCropPipeline:
         torch.cuda.current_stream(self.device).synchronize()
         return h
 
+    def run_host_stream(self, steps: int, refill: Optional[Callable[[dict, int], None]] = None,
+                        on_result: Optional[Callable[[dict, int], None]] = None, consumer=None):
+        """``steps`` passes from pinned host buffers with the uploads double buffered.
+
+        The host->device copy of step k+1 runs on a copy stream while step k computes, and the device->host
+        read of step k is collected one step later, so in steady state a step costs max(compute, copies)
+        instead of their sum.  ``refill(host_buffers, k)`` is called before step k is uploaded (the buffers are
+        reusable then); ``on_result(results, k)`` receives the pinned result tensors of step k.  Every step's
+        inputs are copied H2D and every step's results D2H.
+        """
+        h, d = self._host
+        dev = self.device
+        if not hasattr(self, '_stream_state'):
+            d2 = {k: torch.empty_like(v) for k, v in d.items()}
+            res_keys = ('idx', 'n', 'cost', 'X', 'n_rois')
+            h2 = {k: torch.empty_like(h[k]).pin_memory() for k in res_keys}
+            self._stream_state = {'d': (d, d2), 'hres': ({k: h[k] for k in res_keys}, h2),
+                                  'copy': torch.cuda.Stream(device=dev)}
+        st = self._stream_state
+        main = torch.cuda.current_stream(dev)
+        up_done = [torch.cuda.Event(), torch.cuda.Event()]        # upload into set j finished
+        free = [torch.cuda.Event(), torch.cuda.Event()]           # compute finished reading set j
+        res_done = [torch.cuda.Event(), torch.cuda.Event()]       # results of set j are in pinned memory
+        host_read = [torch.cuda.Event(), torch.cuda.Event()]      # the copy stream finished reading the pinned inputs
+
+        def upload(k):
+            j = k & 1
+            if refill is not None:
+                if k >= 1:
+                    host_read[(k - 1) & 1].synchronize()           # previous upload no longer reads the pinned inputs
+                refill(h, k)
+            with torch.cuda.stream(st['copy']):
+                if k >= 2:
+                    st['copy'].wait_event(free[j])
+                for key, t in st['d'][j].items():
+                    t.copy_(h[key], non_blocking=True)
+                up_done[j].record(st['copy'])
+                host_read[j].record(st['copy'])
+
+        upload(0)
+        for k in range(steps):
+            j = k & 1
+            if k + 1 < steps:
+                upload(k + 1)
+            main.wait_event(up_done[j])
+            dj = st['d'][j]
+            centers = batched.box_centers(dj['boxes'])
+            res, offs = self.run_device(dj['Ks'], dj['RTs'], centers, dj['counts'], dj['boxes'], dj['images'],
+                                        dj['image_of_scene'], consumer=consumer)
+            free[j].record(main)
+            if k >= 2:
+                res_done[j].synchronize()                           # pinned result set j was handed out two steps ago
+            hr = st['hres'][j]
+            hr['idx'].copy_(res.idx, non_blocking=True)
+            hr['n'].copy_(res.n, non_blocking=True)
+            hr['cost'].copy_(res.cost, non_blocking=True)
+            hr['X'].copy_(res.X, non_blocking=True)
+            hr['n_rois'].copy_(offs[self.S:self.S + 1], non_blocking=True)
+            res_done[j].record(main)
+            if k >= 1:                                              # collect step k-1 while step k runs
+                res_done[(k - 1) & 1].synchronize()
+                if on_result is not None:
+                    on_result(st['hres'][(k - 1) & 1], k - 1)
+        res_done[(steps - 1) & 1].synchronize()
+        if on_result is not None:
+            on_result(st['hres'][(steps - 1) & 1], steps - 1)
+        return st['hres'][(steps - 1) & 1]
+
     def h2d_bytes(self) -> int:
         h, d = self._host
         return int(sum(h[k].numel() * h[k].element_size() for k in d))
