@@ -192,7 +192,7 @@ __device__ void match_carve(MatchSmem& ms, unsigned char* p, int Dmax, int nwarp
 // ------------------------------------------------------------------------------------------------------
 // PoseEstimator._match for one scene per CTA
 // ------------------------------------------------------------------------------------------------------
-__global__ void bpc_match_kernel(const float* __restrict__ Ks, const double* __restrict__ RTs,
+__global__ void __launch_bounds__(256, 2) bpc_match_kernel(const float* __restrict__ Ks, const double* __restrict__ RTs,
                                  const double* __restrict__ centers, const int32_t* __restrict__ counts,
                                  int S, int Dmax, float threshold,
                                  int32_t* __restrict__ idx, int32_t* __restrict__ nout, float* __restrict__ costout,
@@ -213,9 +213,6 @@ __global__ void bpc_match_kernel(const float* __restrict__ Ks, const double* __r
         if (tid < 3) {
             const int a = (tid == 2) ? 1 : 0, b = (tid == 0) ? 1 : 2;        // pairs 12, 13, 23
             fundamental(K + a * 9, RT + a * 16, K + b * 9, RT + b * 16, ms.F + tid * 9);
-        } else if (tid >= 32 - 3 && tid < 32) {
-            const int c = tid - (32 - 3);
-            projection(K + c * 9, RT + c * 16, ms.Pm + c * 12);
         }
         __syncthreads();
         if (Fout != nullptr && tid < 27) Fout[(size_t)s * 27 + tid] = ms.F[tid];
@@ -306,18 +303,32 @@ __global__ void bpc_match_kernel(const float* __restrict__ Ks, const double* __r
             const int i = r / M, j = r - i * M;
             const size_t o = (size_t)s * Dmax + rank;
             idx[o * 3 + 0] = i; idx[o * 3 + 1] = j; idx[o * 3 + 2] = k;
-            costout[o] = c;
-            double xy[6];
-            xy[0] = sc.pt(0, i)[0]; xy[1] = sc.pt(0, i)[1];
-            xy[2] = sc.pt(1, j)[0]; xy[3] = sc.pt(1, j)[1];
-            xy[4] = sc.pt(2, k)[0]; xy[5] = sc.pt(2, k)[1];
-            double X[3];
-            triangulate3(ms.Pm, xy, X);
-            Xout[o * 3 + 0] = X[0]; Xout[o * 3 + 1] = X[1]; Xout[o * 3 + 2] = X[2];
-            if (reproj != nullptr)
-                for (int v = 0; v < 3; ++v) reproj[o * 3 + v] = reprojection(ms.Pm + v * 12, X, xy + v * 2);
+            costout[o] = c;                  // triangulation of the match: bpc_match_tri_kernel (register budget)
         }
     }
+}
+
+// DLT triangulation + reprojection error of every match written by bpc_match_kernel, one thread per match slot.
+// (A separate launch keeps the 80 live doubles of the Jacobi sweep out of the matcher's register allocation.)
+__global__ void __launch_bounds__(128)
+bpc_match_tri_kernel(const float* __restrict__ Ks, const double* __restrict__ RTs, const double* __restrict__ centers,
+                     const int32_t* __restrict__ idx, const int32_t* __restrict__ n, int S, int Dmax,
+                     double* __restrict__ Xout, double* __restrict__ reproj) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (t >= (long long)S * Dmax) return;
+    const int s = (int)(t / Dmax), slot = (int)(t - (long long)s * Dmax);
+    if (slot >= n[s]) return;
+    double Pm[36], xy[6], X[3];
+    for (int c = 0; c < 3; ++c) {
+        projection(Ks + (size_t)s * 27 + c * 9, RTs + (size_t)s * 48 + c * 16, Pm + c * 12);
+        const int d = idx[(size_t)t * 3 + c];
+        const double* p = centers + (((size_t)s * 3 + c) * Dmax + d) * 2;
+        xy[c * 2] = p[0]; xy[c * 2 + 1] = p[1];
+    }
+    triangulate3(Pm, xy, X);
+    Xout[(size_t)t * 3 + 0] = X[0]; Xout[(size_t)t * 3 + 1] = X[1]; Xout[(size_t)t * 3 + 2] = X[2];
+    if (reproj != nullptr)
+        for (int v = 0; v < 3; ++v) reproj[(size_t)t * 3 + v] = reprojection(Pm + v * 12, X, xy + v * 2);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -639,6 +650,9 @@ extern "C" int bpc_match_triangulate(const float* Ks, const double* RTs, const d
     cudaError_t e = cudaFuncSetAttribute(bpc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     bpc_match_kernel<<<S, threads, smem, (cudaStream_t)stream>>>(Ks, RTs, centers, counts, S, Dmax, threshold, idx, n, cost, X, reproj, F);
+    BPC_LAUNCH_CHECK();
+    const long long slots = (long long)S * Dmax;
+    bpc_match_tri_kernel<<<(unsigned)((slots + 127) / 128), 128, 0, (cudaStream_t)stream>>>(Ks, RTs, centers, idx, n, S, Dmax, X, reproj);
     BPC_LAUNCH_CHECK();
     return BPC_OK;
 }
