@@ -30,7 +30,7 @@ namespace bpc {
 
 constexpr int CROP_BAND = 8;                 // generic kernel: output rows per work item
 constexpr int CROP_RAW_BYTES = 40 * 1024;    // generic kernel: staged source bytes
-constexpr int WARP_BUF = 2560;               // warp kernel: bytes of one staging buffer (two per warp)
+constexpr int WARP_BUF = 3584;               // warp kernel: bytes of one staging buffer (two per warp)
 constexpr int WARP_DESC = 32 * 16;           // warp kernel: 32 row descriptors (two rings per warp)
 constexpr int WARP_SMEM = 2 * WARP_BUF + 2 * WARP_DESC + 16;   // + two mbarriers
 constexpr int WARPK_WARPS = 8;
@@ -176,7 +176,14 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                     g.src = (unsigned long long)(uintptr_t)images + (((unsigned long long)img * H + y1) * W + x1) * 3ull;
                     if (g.regime == 1 && g.scale_x < 2.0 && g.scale_y < 2.0) g.cls = 1;
                     else if (g.regime == 3) g.cls = 3;
-                    else g.cls = 2;
+                    else if (g.regime == 1) {
+                        // general tap counts in the warp kernel if a strip's rows fit its staging buffer:
+                        // 32 columns span at most 31*scale_x + ceil(scale_x) + 2 source pixels
+                        const int seg_px = (int)(31.0 * g.scale_x) + (int)ceil(g.scale_x) + 3;
+                        const int pitch_max = ((3 * seg_px + 46) >> 4) << 4;
+                        const int rows_need = (int)ceil(g.scale_y) + 4;
+                        g.cls = (pitch_max <= 512 && WARP_BUF / pitch_max >= rows_need) ? 4 : 2;
+                    } else g.cls = 2;
                 }
             }
             if (status != nullptr) status[roi] = (g.regime == 0) ? 1 : 0;
@@ -186,10 +193,22 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
     }
     __syncthreads();
     const int cls = g.cls;
-    if (cls != 1 && cls != 3) return;
+    if (cls != 1 && cls != 3 && cls != 4) return;
     float4* xd = xdesc + (size_t)roi * DESC_STRIDE;
     float4* yd = ydesc + (size_t)roi * DESC_STRIDE;
-    if (cls == 1) {
+    if (cls == 4) {
+        // (w_first, w_middle, w_last, bits(start | taps << 24)); a missing first / last tap takes the middle weight
+        for (int axis = 0; axis < 2; ++axis) {
+            const int nd = axis ? g.new_h : g.new_w;
+            if (tid < nd) {
+                int st, n, flags; float af, am, al;
+                area_taps(tid, axis ? g.scale_y : g.scale_x, axis ? g.h : g.w, st, n, af, am, al, flags);
+                const float w0 = (flags & 1) ? af : ((n == 1 && (flags & 2)) ? al : am);
+                const float wl = (flags & 2) ? al : am;
+                (axis ? yd : xd)[tid] = make_float4(w0, am, wl, __int_as_float(st | (n << 24)));
+            }
+        }
+    } else if (cls == 1) {
         if (tid < g.new_w) {
             int xs, xn; float w0, w1, w2;
             area_taps3(tid, g.scale_x, g.w, xs, xn, w0, w1, w2);
@@ -319,6 +338,7 @@ struct ColW {
 
 // shared-memory accesses through 32-bit shared-window addresses (no generic-address arithmetic in the hot loop)
 __device__ __forceinline__ unsigned lds_u32(unsigned addr) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ unsigned lds_u8(unsigned addr) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ float lds_f32(unsigned addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
 __device__ __forceinline__ float4 lds_f4(unsigned addr) {
     float4 v;
@@ -486,10 +506,11 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
         const bool active = xr >= 0 && xr < new_w;
         const bool padlane = !active && x < T;
         const float4 xd = xdesc[(size_t)roi * DESC_STRIDE + min(max(xr, 0), new_w - 1)];
-        const int xs = __float_as_int(xd.w);
+        const int xs = __float_as_int(xd.w) & 0xffffff;
+        const int xn = (cls == 4) ? (__float_as_int(xd.w) >> 24) : 3;     // source pixels read from xs on
         const int xs_min = -warp_max_i32(-xs);
-        const int xs_max = warp_max_i32(xs);
-        const int seg_bytes = 3 * (xs_max + 3 - xs_min);
+        const int xe_max = warp_max_i32(xs + xn);
+        const int seg_bytes = 3 * (xe_max - xs_min);
         const int pitch = ((15 + seg_bytes + 8 + 15) >> 4) << 4;
         const int nv = pitch >> 4;
         const int rpp = 32 / nv, lr = lane / nv, lv = lane - lr * nv;
@@ -511,7 +532,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             const int cnt = min(bh, new_h - b * bh);
             if (lane < cnt) reinterpret_cast<float4*>(wbase + 2 * WARP_BUF + k * WARP_DESC)[lane] = yd;
             int lo, hi;
-            if (cls == 1) {
+            if (cls != 3) {
                 const int ysn = __float_as_int(yd.w);
                 lo = ysn & 0xffffff; hi = lo + (ysn >> 24) - 1;
             } else {
@@ -534,7 +555,74 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
         float4 ydn = load_desc(1);
         int s_lo_next = 0;
 
-        if (cls == 1) {
+        if (cls == 4) {
+            // ---------------- regime 1, any tap count (scale >= 2): scalar loops over the taps ----------------
+            const float w0 = xd.x, wm = xd.y, wl = xd.z;
+            const float c0 = __fmul_rn(w0, -8388608.0f), cm = __fmul_rn(wm, -8388608.0f), cl = __fmul_rn(wl, -8388608.0f);
+            int crow = -1;
+            float hc[3] = {0.f, 0.f, 0.f};
+            auto hrow = [&](unsigned rowaddr, float* h) {      // sequential taps: ((S0*w0 + S1*wm) + ...) + Sl*wl
+#pragma unroll
+                for (int c = 0; c < 3; ++c) h[c] = __fmaf_rn(__uint_as_float(lds_u8(rowaddr + c) + 0x4B000000u), w0, c0);
+                for (int k = 1; k < xn - 1; ++k)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        h[c] = __fadd_rn(h[c], __fmaf_rn(__uint_as_float(lds_u8(rowaddr + 3 * k + c) + 0x4B000000u), wm, cm));
+                if (xn > 1)
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+                        h[c] = __fadd_rn(h[c], __fmaf_rn(__uint_as_float(lds_u8(rowaddr + 3 * (xn - 1) + c) + 0x4B000000u), wl, cl));
+            };
+            for (int b = 0; b < nb; ++b) {
+                const int k = b & 1;
+                if (bulk_cur) {
+                    if (k == 0) { mbar_wait(bar_s, phase0); phase0 ^= 1u; } else { mbar_wait(bar_s + 8, phase1); phase1 ^= 1u; }
+                } else {
+                    cp_async_wait_all();
+                }
+                __syncwarp();
+                if (b + 1 < nb) s_lo_next = stage(b + 1, k ^ 1, ydn);
+                ydn = load_desc(b + 2);
+                const unsigned cur = wbase_s + k * WARP_BUF, ring = wbase_s + 2 * WARP_BUF + k * WARP_DESC;
+                const int y0 = b * bh, cnt = min(bh, new_h - y0);
+                if (active) {
+                    for (int r = 0; r < cnt; ++r) {
+                        const float4 d = lds_f4(ring + r * 16);
+                        const int ysn = __float_as_int(d.w);
+                        const int ys = ysn & 0xffffff, n = ysn >> 24;
+                        float acc[3];
+                        for (int t = 0; t < n; ++t) {
+                            const int row = ys + t;
+                            if (row != crow) {
+                                int a = (row - s_lo_cur) * pitch + colc;
+                                if (!ALIGNED) a += (mis0 + row * misstep) & 15;
+                                hrow(cur + a, hc);
+                                crow = row;
+                            }
+                            const float beta = (t == 0) ? d.x : ((t == n - 1) ? d.z : d.y);
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                const float term = __fmul_rn(beta, hc[c]);
+                                acc[c] = (t == 0) ? term : __fadd_rn(acc[c], term);
+                            }
+                        }
+                        const int o0 = round_u8(acc[0]), o1 = round_u8(acc[1]), o2 = round_u8(acc[2]);
+                        if (OUT_U8) {
+                            out.px(roi, dy0 + y0 + r, x, o0, o1, o2);
+                        } else {
+                            optr[0] = lds_f32(lut_s + 4 * (swap ? o2 : o0));
+                            optr[plane] = lds_f32(lut_s + 1024 + 4 * o1);
+                            optr[2 * plane] = lds_f32(lut_s + 2048 + 4 * (swap ? o0 : o2));
+                            optr += T;
+                        }
+                    }
+                } else if (padlane) {
+                    for (int r = 0; r < cnt; ++r) out.pad(roi, dy0 + y0 + r, x);
+                }
+                s_lo_cur = s_lo_next;
+                bulk_cur = bulk_next;
+            }
+        } else if (cls == 1) {
             ColW cw;
             cw.set(xd.x, xd.y, xd.z);
             int crow = -1;
