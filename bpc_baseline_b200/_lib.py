@@ -31,6 +31,7 @@ SIGNATURES = {
     'bpc_epipolar_error_full': (_i, [_p, _p, _i, _p, _p]),
     'bpc_triangulate_views': (_i, [_p, _p, _i, _i, _p, _p]),
     'bpc_box_centers': (_i, [_p, _i, _p, _p]),
+    'bpc_detections_from_yolo': (_i, [_p, _p, _p, _p, _i, _i, _f, _i, _p, _p, _p, _p]),
     'bpc_build_rois': (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     'bpc_roi_crop_workspace_bytes': (_sz, [_i]),
     'bpc_roi_crop': (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),

@@ -64,6 +64,29 @@ def fundamental(Ks: torch.Tensor, RTs: torch.Tensor) -> torch.Tensor:
     return F
 
 
+def detections_from_yolo(xyxy: torch.Tensor, conf: torch.Tensor, cls: torch.Tensor, nraw: torch.Tensor,
+                         conf_thresh: float, Dmax: int):
+    """Detector outputs -> the matcher's detection tensors (process_pose.py:123-141), all on the device.
+
+    xyxy f32 [S,3,Nraw,4], conf / cls f32 [S,3,Nraw], nraw i32 [S,3] -> (boxes i32 [S,3,Dmax,4],
+    centers f64 [S,3,Dmax,2], counts i32 [S,3]); counts above Dmax mean detections were dropped.
+    """
+    _chk(xyxy, torch.float32, 'xyxy', 4); _chk(conf, torch.float32, 'conf', 3); _chk(cls, torch.float32, 'cls', 3)
+    _chk(nraw, torch.int32, 'nraw', 2)
+    S, C, N, _ = xyxy.shape
+    if xyxy.shape[3] != 4 or tuple(conf.shape) != (S, C, N) or tuple(cls.shape) != (S, C, N) or tuple(nraw.shape) != (S, C):
+        raise RuntimeError('expected xyxy [S,C,Nraw,4], conf / cls [S,C,Nraw], nraw [S,C]')
+    dev = xyxy.device
+    boxes = torch.zeros((S, C, Dmax, 4), dtype=torch.int32, device=dev)
+    centers = torch.zeros((S, C, Dmax, 2), dtype=torch.float64, device=dev)
+    counts = torch.empty((S, C), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().bpc_detections_from_yolo(_p(xyxy), _p(conf), _p(cls), _p(nraw), S * C, N,
+                                                        float(np.float32(conf_thresh)), int(Dmax), _p(boxes), _p(centers),
+                                                        _p(counts), _stream(dev)), 'bpc_detections_from_yolo')
+    return boxes, centers, counts
+
+
 def box_centers(boxes: torch.Tensor) -> torch.Tensor:
     """centres f64 [..., 2] from int32 boxes [..., 4] (process_pose.py:134-136)."""
     _chk(boxes, torch.int32, 'boxes')

@@ -535,6 +535,33 @@ __global__ void bpc_reproj_kernel(const double* __restrict__ P, const double* __
     err[t] = reprojection(Pm, X + (size_t)m * 3, pts + (size_t)t * 2);
 }
 
+// Detector post-processing (process_pose.py:123-141): keep class 0 with conf >= threshold, int() every box
+// coordinate (truncation toward zero), centre = 0.5 * (x1 + x2); order preserved.  One warp per (scene, camera).
+__global__ void bpc_detections_kernel(const float* __restrict__ xyxy, const float* __restrict__ conf, const float* __restrict__ cls,
+                                      const int32_t* __restrict__ nraw, int SC, int Nraw, float thresh, int Dmax,
+                                      int32_t* __restrict__ boxes, double* __restrict__ centers, int32_t* __restrict__ counts) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= SC) return;
+    const int n = min(max(nraw[w], 0), Nraw);
+    int kept = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int d = base + lane;
+        bool keep = false;
+        if (d < n) keep = (cls[(size_t)w * Nraw + d] == 0.f) && (conf[(size_t)w * Nraw + d] >= thresh);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        const int pos = kept + __popc(m & ((1u << lane) - 1));
+        if (keep && pos < Dmax) {
+            const float4 b = reinterpret_cast<const float4*>(xyxy)[(size_t)w * Nraw + d];
+            const int x1 = __float2int_rz(b.x), y1 = __float2int_rz(b.y), x2 = __float2int_rz(b.z), y2 = __float2int_rz(b.w);
+            reinterpret_cast<int4*>(boxes)[(size_t)w * Dmax + pos] = make_int4(x1, y1, x2, y2);
+            centers[((size_t)w * Dmax + pos) * 2 + 0] = 0.5 * (double)((long long)x1 + x2);
+            centers[((size_t)w * Dmax + pos) * 2 + 1] = 0.5 * (double)((long long)y1 + y2);
+        }
+        kept += __popc(m);
+    }
+    if (lane == 0) counts[w] = kept;          // may exceed Dmax: the caller sees the overflow
+}
+
 __global__ void bpc_box_centers_kernel(const int32_t* __restrict__ boxes, int count, double* __restrict__ centers) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= count) return;
@@ -701,6 +728,18 @@ extern "C" int bpc_triangulate_views(const double* P, const double* pts, int n, 
     if (n < 0 || V < 2 || V > 8 || (n > 0 && (!P || !pts || !X))) return BPC_EINVAL;
     if (n == 0) return BPC_OK;
     bpc_triangulate_views_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(P, pts, n, V, X);
+    BPC_LAUNCH_CHECK();
+    return BPC_OK;
+}
+
+extern "C" int bpc_detections_from_yolo(const float* xyxy, const float* conf, const float* cls, const int32_t* nraw, int SC, int Nraw,
+                                        float conf_thresh, int Dmax, int32_t* boxes, double* centers, int32_t* counts, void* stream) {
+    if (SC < 0 || Nraw < 1 || Dmax < 1) return BPC_EINVAL;
+    if (SC > 0 && (!xyxy || !conf || !cls || !nraw || !boxes || !centers || !counts)) return BPC_EINVAL;
+    if ((((uintptr_t)xyxy) & 15) != 0 || (((uintptr_t)boxes) & 15) != 0) return BPC_EALIGN;
+    if (SC == 0) return BPC_OK;
+    bpc_detections_kernel<<<(SC * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(xyxy, conf, cls, nraw, SC, Nraw, conf_thresh, Dmax,
+                                                                                    boxes, centers, counts);
     BPC_LAUNCH_CHECK();
     return BPC_OK;
 }

@@ -135,6 +135,16 @@ int bpc_triangulate_views(const double* P, const double* pts, int n, int V, doub
 /* Centres from integer boxes: cx = 0.5*(x1+x2), cy = 0.5*(y1+y2), process_pose.py:134-136. */
 int bpc_box_centers(const int32_t* boxes, int count, double* centers, void* stream);
 
+/* Detector post-processing (producer side of the path): class / confidence filter,
+ * int() truncation of the box, centre -- the loop of PoseEstimator._detect, bpc/inference/process_pose.py:123-141,
+ * producing the device-resident detection tensors the matcher consumes.
+ *   xyxy float [SC][Nraw][4] (16-byte aligned), conf / cls float [SC][Nraw], nraw int32 [SC]; SC = scenes * cameras
+ *   keeps cls == 0 && conf >= conf_thresh, in order; boxes int32 [SC][Dmax][4], centers double [SC][Dmax][2]
+ *   counts int32 [SC] = number kept (entries beyond Dmax are dropped; counts > Dmax signals the overflow)
+ */
+int bpc_detections_from_yolo(const float* xyxy, const float* conf, const float* cls, const int32_t* nraw, int SC, int Nraw,
+                             float conf_thresh, int Dmax, int32_t* boxes, double* centers, int32_t* counts, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * ROI records for the crop kernel from the matcher's output: 3 per match in (scene, match, view)
  * order, rois int32 [R][5] = (image index, x1, y1, x2, y2).  Mirrors the loops of
