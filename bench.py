@@ -94,11 +94,13 @@ class ClockSampler:
             return
         def pump():
             for line in self.proc.stdout:
-                self.rows.append(line.strip())
+                self.rows.append((time.time(), line.strip()))
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """Summary of the samples that arrived inside the timed region [t0, t1] (host clock); if the region was
+        shorter than the sampling period, of the samples taken under load since warm-up began."""
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -108,7 +110,12 @@ class ClockSampler:
             self.proc.kill()
         sm, smmax, power, reasons = [], [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for row in self.rows:
+        rows = [r for (ts, r) in self.rows if t0 is None or t0 <= ts <= t1 + 0.12]
+        scope = 'timed region'
+        if not rows:
+            rows = [r for (ts, r) in self.rows[1:]]
+            scope = 'warm-up + timed region (timed region shorter than the 100 ms sampling period)'
+        for row in rows:
             parts = [p.strip() for p in row.split(',')]
             if len(parts) < 7:
                 continue
@@ -122,7 +129,7 @@ class ClockSampler:
         if not sm:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
         return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(smmax)), 'power_w_max': float(max(power)),
-                'samples': len(sm), 'reasons': sorted(reasons)}
+                'samples': len(sm), 'scope': scope, 'reasons': sorted(reasons)}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -285,17 +292,18 @@ def main():
         if world > 1:                     # final gather of the pose records over NVLink
             distributed.gather_records(distributed.pack_records(r.idx, r.n, r.cost, r.X))
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = _lib.launch_count()
     t_start, t_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    wall0 = time.time()
     t_start.record()
     for k in range(args.steps):
         step(k)
@@ -303,7 +311,8 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    wall1 = time.time()
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     launches = _lib.launch_count() - launches0
     ms = t_start.elapsed_time(t_stop)
     crop_ms = sum(e[1].elapsed_time(e[2]) for e in ev)

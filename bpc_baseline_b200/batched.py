@@ -256,6 +256,7 @@ def normalise_lut(device, mean: Sequence[float] = MEAN, std: Sequence[float] = S
 
 
 _WS_CACHE: dict = {}
+MAX_ROIS_PER_LAUNCH = 16384
 
 
 def _crop_workspace(dev, R: int) -> torch.Tensor:
@@ -304,10 +305,14 @@ def roi_crop(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(255, 
         _chk(status, torch.int32, 'status', 1)
     if n_rois is not None:
         _chk(n_rois, torch.int32, 'n_rois')
-    ws = _crop_workspace(dev, R)
+    ws = _crop_workspace(dev, min(R, MAX_ROIS_PER_LAUNCH))
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().bpc_roi_crop(_p(images), B, H, W, _p(rois), R, _p(n_rois), int(roi_first), int(T), f, int(bool(swap_rb)),
-                                            _p(lut), _p(out), _p(status), _p(ws), ws.numel(), _stream(dev)), 'bpc_roi_crop')
+        for lo in range(0, R, MAX_ROIS_PER_LAUNCH):          # bounds the scratch (8.3 KB of tap descriptors per ROI)
+            r = min(MAX_ROIS_PER_LAUNCH, R - lo)
+            _lib.check(_lib.load().bpc_roi_crop(_p(images), B, H, W, _p(rois[lo:lo + r]), r, _p(n_rois), int(roi_first) + lo, int(T),
+                                                f, int(bool(swap_rb)), _p(lut), _p(out[lo:lo + r]),
+                                                _p(status[lo:lo + r]) if status is not None else None,
+                                                _p(ws), ws.numel(), _stream(dev)), 'bpc_roi_crop')
     return out
 
 
@@ -321,8 +326,11 @@ def roi_crop_u8(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(25
         out = torch.empty((R, T, T, 3), dtype=torch.uint8, device=dev)
     if status is not None:
         _chk(status, torch.int32, 'status', 1)
-    ws = _crop_workspace(dev, R)
+    ws = _crop_workspace(dev, min(R, MAX_ROIS_PER_LAUNCH))
     with torch.cuda.device(dev):
-        _lib.check(_lib.load().bpc_roi_crop_u8(_p(images), B, H, W, _p(rois), R, _p(n_rois), int(roi_first), int(T), f, _p(out), _p(status),
-                                               _p(ws), ws.numel(), _stream(dev)), 'bpc_roi_crop_u8')
+        for lo in range(0, R, MAX_ROIS_PER_LAUNCH):
+            r = min(MAX_ROIS_PER_LAUNCH, R - lo)
+            _lib.check(_lib.load().bpc_roi_crop_u8(_p(images), B, H, W, _p(rois[lo:lo + r]), r, _p(n_rois), int(roi_first) + lo, int(T),
+                                                   f, _p(out[lo:lo + r]), _p(status[lo:lo + r]) if status is not None else None,
+                                                   _p(ws), ws.numel(), _stream(dev)), 'bpc_roi_crop_u8')
     return out

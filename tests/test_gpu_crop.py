@@ -110,3 +110,27 @@ def test_build_rois_matches_host_mirror():
     assert offs[-1] == len(want)
     assert np.array_equal(rois.cpu().numpy()[:offs[-1]], want)
     assert np.array_equal(offs[:-1], np.concatenate([[0], np.cumsum(3 * res.n.cpu().numpy())[:-1]]))
+
+
+def test_long_roi_lists_are_split_into_launches(monkeypatch):
+    """More ROIs than one launch's scratch covers: the wrapper splits the list; roi_first / n_rois keep working."""
+    from bpc_baseline_b200 import batched, synth
+    imgs = synth.make_images(1, seed=8, width=800, height=600)
+    rng = np.random.default_rng(8)
+    rois = []
+    for _ in range(23):
+        w, h = rng.integers(16, 500, 2)
+        x1 = int(rng.integers(0, 800 - w + 1)); y1 = int(rng.integers(0, 600 - h + 1))
+        rois.append((0, x1, y1, x1 + int(w), y1 + int(h)))
+    rois = np.asarray(rois, np.int32)
+    whole = batched.roi_crop_u8(to_dev(imgs), to_dev(rois), T=96).cpu().numpy()
+    monkeypatch.setattr(batched, 'MAX_ROIS_PER_LAUNCH', 5)
+    status = torch.full((23,), -1, dtype=torch.int32, device='cuda')
+    split = batched.roi_crop_u8(to_dev(imgs), to_dev(rois), T=96, status=status).cpu().numpy()
+    assert np.array_equal(whole, split) and int(status.sum()) == 0
+    out = torch.full((23, 3, 96, 96), 7.0, device='cuda')
+    batched.roi_crop(to_dev(imgs), to_dev(rois), T=96, n_rois=torch.tensor([13], dtype=torch.int32, device='cuda'), out=out)
+    assert bool((out[13:] == 7.0).all()) and not bool((out[:13] == 7.0).all(dim=(1, 2, 3)).any())
+    for r in (0, 7, 12):
+        want = ocrop.crop_tensor_ref(imgs[0], rois[r, 1:], target_size=96)
+        assert np.array_equal(out[r].cpu().numpy().view(np.uint32), want.view(np.uint32))
