@@ -373,6 +373,8 @@ __device__ __forceinline__ void h_lin(unsigned a4, int sh, int w0, int w1, int* 
 // cvRound(v) for 0 <= v < 2^22 without F2I: adding 2^23 leaves round-half-even(v) in the low mantissa bits
 // (no clamp: the tap weights of each axis sum to 1 within a few ulp, so v <= 255.001 and the result is <= 255)
 __device__ __forceinline__ int round_u8(float v) { return __float_as_int(__fadd_rn(v, 8388608.0f)) & 0xff; }
+// shared address of LUT[cvRound(v)]: lut_m = lut_base - 4 * 0x4B000000 (mod 2^32)
+__device__ __forceinline__ unsigned lut_addr(float v, unsigned lut_m) { return (unsigned)__float_as_int(__fadd_rn(v, 8388608.0f)) * 4u + lut_m; }
 
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier in shared memory ----
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -457,6 +459,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
     unsigned char* wbase = smem + 768 * 4 + wid * WARP_SMEM;          // [2][WARP_BUF] staging, then [2][32] float4 row descriptors
     const unsigned wbase_s = (unsigned)__cvta_generic_to_shared(wbase), lut_s = (unsigned)__cvta_generic_to_shared(smem);
 
+    const unsigned lut_m = lut_s - 4u * 0x4B000000u;                    // see lut_addr()
     const unsigned bar_s = wbase_s + 2 * WARP_BUF + 2 * WARP_DESC;     // two mbarriers, one per staging buffer
     if (lane == 0) { mbar_init(bar_s, 1); mbar_init(bar_s + 8, 1); }
     unsigned phase0 = 0, phase1 = 0;                                      // parity of the next completion of each barrier
@@ -670,13 +673,14 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                         crow = ys + n - 1;
                         float a0f, a1f;
                         unpack2(acc01, a0f, a1f);
-                        const int o0 = round_u8(a0f), o1 = round_u8(a1f), o2 = round_u8(acc2);
                         if (OUT_U8) {
-                            out.px(roi, dy0 + y0 + r, x, o0, o1, o2);
+                            out.px(roi, dy0 + y0 + r, x, round_u8(a0f), round_u8(a1f), round_u8(acc2));
                         } else {
-                            optr[0] = lds_f32(lut_s + 4 * (swap ? o2 : o0));
-                            optr[plane] = lds_f32(lut_s + 1024 + 4 * o1);
-                            optr[2 * plane] = lds_f32(lut_s + 2048 + 4 * (swap ? o0 : o2));
+                            // bits(v + 2^23) = 0x4B000000 + cvRound(v): the LUT address is one multiply-add away
+                            const unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
+                            optr[0] = lds_f32(swap ? l2 : l0);
+                            optr[plane] = lds_f32(l1 + 1024);
+                            optr[2 * plane] = lds_f32((swap ? l0 : l2) + 2048);
                             optr += T;
                         }
                     }

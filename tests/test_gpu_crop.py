@@ -65,6 +65,8 @@ def test_random_boxes_all_regimes_full_res():
         w, h = rng.integers(8, 900, 2)
         x1 = int(rng.integers(0, 1920 - w + 1)); y1 = int(rng.integers(0, 1080 - h + 1))
         rois.append((int(rng.integers(0, 2)), x1, y1, x1 + int(w), y1 + int(h)))
+    # bottom-right corner of the LAST image of the pool: the staging code must not read past the allocation
+    rois += [(1, 1700, 900, 1920, 1080), (1, 1500, 700, 1920, 1080), (1, 1000, 300, 1920, 1080), (1, 1912, 1000, 1920, 1080)]
     rois += [(1, 0, 0, 1920, 1080), (0, 1919 - 8, 1080 - 9, 1919, 1080), (1, 0, 0, 448, 448), (0, 5, 5, 5 + 672, 5 + 448),
              (0, 0, 0, 224, 224), (1, 100, 100, 100 + 224, 100 + 112)]
     rois = np.asarray(rois, np.int32)
