@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument('--dets', type=int, default=20, help='detections per camera')
     ap.add_argument('--target', type=int, default=224, help='crop side T')
     ap.add_argument('--pool', type=int, default=8, help='image pool: number of 3-view full-resolution triplets')
-    ap.add_argument('--chunk-rois', type=int, default=8192)
+    ap.add_argument('--chunk-rois', type=int, default=16384, help='ROIs per crop launch (16384 x 602 KB = 9.9 GB chunk buffer)')
     ap.add_argument('--p-drop', type=float, default=0.0)
     ap.add_argument('--sigma', type=float, default=1.0)
     ap.add_argument('--no-crops', action='store_true', help='geometry only (dense-bin experiments)')

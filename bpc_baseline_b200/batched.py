@@ -256,7 +256,7 @@ def normalise_lut(device, mean: Sequence[float] = MEAN, std: Sequence[float] = S
 
 
 _WS_CACHE: dict = {}
-MAX_ROIS_PER_LAUNCH = 16384
+MAX_ROIS_PER_LAUNCH = 32768
 
 
 def _crop_workspace(dev, R: int) -> torch.Tensor:

@@ -20,7 +20,7 @@ from . import batched
 
 
 class MatchCropPipeline:
-    def __init__(self, S: int, Dmax: int, *, T: int = 224, chunk_rois: int = 8192, threshold=30,
+    def __init__(self, S: int, Dmax: int, *, T: int = 224, chunk_rois: int = 16384, threshold=30,
                  swap_rb: bool = True, fill=(255, 255, 255), device='cuda', want_reproj: bool = True):
         self.S, self.D, self.T = int(S), int(Dmax), int(T)
         self.device = torch.device(device)

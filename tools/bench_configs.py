@@ -76,7 +76,7 @@ def config4(lo, hi, T, R, B=8):
     w = rng.integers(lo, hi, R); h = rng.integers(lo, hi, R)
     x1 = (rng.random(R) * (synth.IMG_W - w)).astype(np.int64); y1 = (rng.random(R) * (synth.IMG_H - h)).astype(np.int64)
     rois = np.stack([rng.integers(0, B * 3, R), x1, y1, x1 + w, y1 + h], axis=1).astype(np.int32)
-    chunk = 8192
+    chunk = 16384
     out = torch.empty((chunk, 3, T, T), dtype=torch.float32, device='cuda')
     drois = dev(rois)
 
@@ -95,7 +95,7 @@ def config5(S=131072, D=20, T=224, pool=8):
     images = dev(synth.make_images(pool * 3))
     ios = dev(((np.arange(S)[:, None] % pool) * 3 + np.arange(3)[None, :]).astype(np.int32))
     Ks, RTs, cen, cnt, boxes = dev(batch.Ks), dev(batch.RTs), dev(batch.centers), dev(batch.counts), dev(batch.boxes)
-    pipe = pipeline.MatchCropPipeline(S, D, T=T, chunk_rois=8192)
+    pipe = pipeline.MatchCropPipeline(S, D, T=T, chunk_rois=16384)
     res, offs = pipe.run_device(Ks, RTs, cen, cnt, boxes, images, ios)
     n_rois = int(offs[-1])
     ms = timed(lambda: pipe.run_device(Ks, RTs, cen, cnt, boxes, images, ios, n_rois_host=n_rois), warm=1, reps=2)
