@@ -122,3 +122,18 @@ def test_install_only_touches_imported_modules(lib):
     finally:
         pkg.uninstall()
         sys.modules.pop('fakeref.inference.epipolar_matching', None)
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/bpc_b200.h must be consumable from C (the boundary is a C ABI, not C++)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which('gcc')
+    if gcc is None:
+        pytest.skip('gcc not available')
+    src = tmp_path / 'use_header.c'
+    src.write_text('#include "bpc_b200.h"\n'
+                   'int probe(void) { return bpc_abi_version() == BPC_ABI_VERSION && BPC_OK == 0 ? (int)sizeof(size_t) : -1; }\n')
+    res = subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-pedantic', '-I', os.path.join(ROOT, 'include'), '-c', str(src),
+                          '-o', str(tmp_path / 'use_header.o')], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
