@@ -50,7 +50,7 @@ def parse_args():
     ap.add_argument('--p-drop', type=float, default=0.0)
     ap.add_argument('--sigma', type=float, default=1.0)
     ap.add_argument('--no-crops', action='store_true', help='geometry only (dense-bin experiments)')
-    ap.add_argument('--cpu-scenes', type=int, default=48, help='scenes in the bounded CPU-baseline sample')
+    ap.add_argument('--cpu-scenes', type=int, default=256, help='scenes in the bounded CPU-baseline sample (~12 s on one core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     return ap.parse_args()

@@ -174,3 +174,33 @@ def test_rejects_cpu_tensors_and_missing_library():
     from bpc_baseline_b200 import batched
     with pytest.raises(RuntimeError):
         batched.fundamental(torch.zeros(1, 3, 3, 3), torch.zeros(1, 3, 4, 4, dtype=torch.float64))
+
+
+def test_skewed_intrinsics_general_inverse():
+    """K with skew takes the general float32 inverse (Gauss-Jordan; LAPACK's last bit is not guaranteed):
+    F within 1e-5 relative of the reference formula, same matches on clean scenes."""
+    from bpc_baseline_b200 import batched, synth
+    batch = synth.make_scenes(16, 8, seed=synth.SEED + 61)
+    batch.Ks[:, :, 0, 1] = np.float32(3.5)                     # skew
+    Ks, RTs, centers, boxes, counts = batch_to_dev(batch)
+    res = batched.match_triangulate(Ks, RTs, centers, counts, 30, want_F=True)
+    F = res.F.cpu().numpy(); idx = res.idx.cpu().numpy(); n = res.n.cpu().numpy()
+    for s in range(16):
+        Kl, RTl = batch.capture_arrays(s)
+        want = og.match_scene(Kl, RTl, [batch.centers[s, c, :batch.counts[s, c]] for c in range(3)], 30)
+        np.testing.assert_allclose(F[s], want['F'], rtol=1e-5, atol=1e-9)
+        assert int(n[s]) == len(want['idx']) and np.array_equal(idx[s, :n[s]], want['idx'])
+
+
+@pytest.mark.parametrize('threshold', [0.5, 2.25, 12.5, 1e9])
+def test_threshold_is_compared_in_float32(threshold):
+    """`val < threshold` on float32 costs (epipolar_matching.py:110-111; NumPy >= 2 compares in float32)."""
+    from bpc_baseline_b200 import batched, synth
+    batch = synth.make_scenes(24, 9, seed=synth.SEED + 62, p_drop=0.2, sigma=3.0)
+    Ks, RTs, centers, boxes, counts = batch_to_dev(batch)
+    res = batched.match_triangulate(Ks, RTs, centers, counts, threshold)
+    idx = res.idx.cpu().numpy(); n = res.n.cpu().numpy()
+    for s in range(24):
+        Kl, RTl = batch.capture_arrays(s)
+        want = og.match_scene(Kl, RTl, [batch.centers[s, c, :batch.counts[s, c]] for c in range(3)], threshold)
+        assert int(n[s]) == len(want['idx']) and np.array_equal(idx[s, :n[s]], want['idx'])
