@@ -8,20 +8,22 @@ import numpy as np
 
 from ... import _host, batched
 
+_FIELDS = (('K', 'cam_K', (3, 3)), ('R', 'cam_R_w2c', (3, 3)), ('t', 'cam_t_w2c', (-1,)))
+
 
 def load_camera_params(scene_dir, cam_ids):
-    """BOP scene_camera_*.json loader -- reference camera_utils.py:6-20 (host I/O, no arithmetic)."""
+    """BOP ``scene_camera_<cam>.json`` -> {cam: {'K' | 'R' | 't': {image_id: float32 array}}}.
+
+    Same structure and dtypes as the reference loader (camera_utils.py:6-20): K and R are 3x3, t is flat, all
+    float32 -- which is what makes R and t reach the matcher as float32-rounded values.  Host I/O only.
+    """
     params = {}
-    cid = None
-    for cid in cam_ids:
-        with open(os.path.join(scene_dir, f"scene_camera_{cid}.json")) as f:
-            data = json.load(f)
-        params[cid] = {'K': {}, 'R': {}, 't': {}}
-        for im_id_str, vals in data.items():
-            im_id = int(im_id_str)
-            params[cid]['K'][im_id] = np.array(vals['cam_K'], dtype=np.float32).reshape(3, 3)
-            params[cid]['R'][im_id] = np.array(vals['cam_R_w2c'], dtype=np.float32).reshape(3, 3)
-            params[cid]['t'][im_id] = np.array(vals['cam_t_w2c'], dtype=np.float32).flatten()
+    for cam in cam_ids:
+        with open(os.path.join(scene_dir, f"scene_camera_{cam}.json")) as fh:
+            per_image = json.load(fh)
+        params[cam] = {name: {int(image_id): np.asarray(entry[key], dtype=np.float32).reshape(shape)
+                              for image_id, entry in per_image.items()}
+                       for name, key, shape in _FIELDS}
     return params
 
 

@@ -27,12 +27,10 @@ def compute_reprojection_error(P, X, point_2d):
 
 
 def compute_final_pose(final_pose_array, triangulated_points):
-    """[Rx, Ry, Rz] mean over cameras + translation -- reference utils/triangulation.py:20-45 (host glue,
-    not on the hot path; no caller in the reference)."""
-    final_pose_array = np.asarray(final_pose_array)
-    num_objects = final_pose_array.shape[0]
-    final_6d_pose = np.zeros((num_objects, 6), dtype=np.float32)
-    for i in range(num_objects):
-        final_6d_pose[i, :3] = final_pose_array[i, :, :3].mean(axis=0)
-        final_6d_pose[i, 3:] = triangulated_points[i]
-    return final_6d_pose
+    """(N, 6) float32 rows [mean Rx, Ry, Rz over the cameras | X, Y, Z] -- reference utils/triangulation.py:20-45
+    (host glue with no caller in the reference; off the hot path)."""
+    angles = np.asarray(final_pose_array)[:, :, :3]
+    pose = np.empty((angles.shape[0], 6), dtype=np.float32)
+    pose[:, :3] = angles.mean(axis=1)
+    pose[:, 3:] = np.asarray(triangulated_points)[:angles.shape[0]]
+    return pose

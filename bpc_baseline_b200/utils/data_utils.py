@@ -52,29 +52,29 @@ def calc_pose_matrix(R_mat, t):
     return pose
 
 
+def _read_json(path):
+    with open(path) as fh:
+        return json.load(fh)
+
+
 def load_gt_poses(scene_dir, scene_id, cam_ids, image_id, obj_id):
-    """Ground-truth poses of one object in the first camera -- reference data_utils.py:355-380 (host I/O)."""
-    gt_poses = []
-    scene_path = os.path.join(scene_dir, scene_id)
-    for cam_id in cam_ids[:1]:
-        gt_path = os.path.join(scene_path, f"scene_gt_{cam_id}.json")
-        info_path = os.path.join(scene_path, f"scene_gt_info_{cam_id}.json")
-        if not os.path.exists(gt_path) or not os.path.exists(info_path):
-            continue
-        with open(gt_path, "r") as f:
-            gt_data = json.load(f)
-        with open(info_path, "r") as f:
-            info_data = json.load(f)
-        img_key = str(image_id)
-        if img_key not in gt_data or img_key not in info_data:
-            continue
-        for obj, _bbox in zip(gt_data[img_key], info_data[img_key]):
-            if obj["obj_id"] != obj_id:
-                continue
-            rotation_matrix = np.array(obj["cam_R_m2c"], dtype=np.float32).reshape(3, 3)
-            translation = np.array(obj["cam_t_m2c"], dtype=np.float32)
-            gt_poses.append(calc_pose_matrix(rotation_matrix, translation))
-    return gt_poses
+    """4x4 ground-truth poses of object ``obj_id`` in image ``image_id`` of the FIRST camera only, or [] when the
+    scene_gt / scene_gt_info files or the image entry are missing -- behaviour of reference data_utils.py:355-380."""
+    cam = list(cam_ids)[0] if len(cam_ids) else None
+    if cam is None:
+        return []
+    base = os.path.join(scene_dir, scene_id)
+    gt_file, info_file = (os.path.join(base, f"{stem}_{cam}.json") for stem in ("scene_gt", "scene_gt_info"))
+    if not (os.path.exists(gt_file) and os.path.exists(info_file)):
+        return []
+    gt, info = _read_json(gt_file), _read_json(info_file)
+    key = str(image_id)
+    if key not in gt or key not in info:
+        return []
+    entries = gt[key][:len(info[key])]                      # the reference zips the two lists
+    return [calc_pose_matrix(np.asarray(e["cam_R_m2c"], dtype=np.float32).reshape(3, 3),
+                             np.asarray(e["cam_t_m2c"], dtype=np.float32))
+            for e in entries if e["obj_id"] == obj_id]
 
 
 class Capture:
@@ -90,13 +90,14 @@ class Capture:
 
     @classmethod
     def from_dir(cls, scene_dir, cam_ids, image_id, obj_id):
+        """Read one capture from a BOP scene directory (reference data_utils.py:399-409): intrinsics / extrinsics from
+        scene_camera_<cam>.json, the image ``rgb_<cam>/<image_id:06d>.{png,jpg}`` per camera, RT as float64 4x4."""
         import cv2                                        # image decoding only (host I/O)
-        cam_params = load_camera_params(scene_dir, cam_ids)
-        Ks = [cam_params[x]['K'][image_id] for x in cam_ids]
-        Rs = [cam_params[x]['R'][image_id] for x in cam_ids]
-        Ts = [cam_params[x]['t'][image_id] for x in cam_ids]
-        RTs = [calc_pose_matrix(r, t) for r, t in zip(Rs, Ts)]
-        image_paths = [glob.glob(os.path.join(scene_dir, f"rgb_{cam_id}", f"{image_id:06d}.*g"))[0] for cam_id in cam_ids]
-        images = [cv2.imread(x) for x in image_paths]
-        gt_poses = load_gt_poses(scene_dir, '', cam_ids, image_id, obj_id)
-        return cls(images, Ks, RTs, obj_id, gt_poses)
+        cams = load_camera_params(scene_dir, cam_ids)
+        Ks = [cams[c]['K'][image_id] for c in cam_ids]
+        RTs = [calc_pose_matrix(cams[c]['R'][image_id], cams[c]['t'][image_id]) for c in cam_ids]
+        images = []
+        for c in cam_ids:
+            hits = glob.glob(os.path.join(scene_dir, f"rgb_{c}", f"{image_id:06d}.*g"))
+            images.append(cv2.imread(hits[0]))
+        return cls(images, Ks, RTs, obj_id, load_gt_poses(scene_dir, '', cam_ids, image_id, obj_id))

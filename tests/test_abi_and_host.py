@@ -137,3 +137,35 @@ def test_header_is_plain_c(tmp_path):
     res = subprocess.run([gcc, '-std=c99', '-Wall', '-Werror', '-pedantic', '-I', os.path.join(ROOT, 'include'), '-c', str(src),
                           '-o', str(tmp_path / 'use_header.o')], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
+
+
+def test_bop_directory_io(tmp_path):
+    """load_camera_params / load_gt_poses / Capture.from_dir: structure and dtypes of the reference loaders
+    (camera_utils.py:6-20, data_utils.py:355-409) -- float32 K / R / t, float64 4x4 RT, first camera's GT only."""
+    import json
+    import cv2
+    from bpc_baseline_b200.inference.utils.camera_utils import load_camera_params
+    from bpc_baseline_b200.utils.data_utils import Capture, load_gt_poses
+    d = str(tmp_path)
+    cams = ['cam1', 'cam2', 'cam3']
+    for c, cid in enumerate(cams):
+        entry = lambda f, t: {'cam_K': [f, 0, 2, 0, f, 3, 0, 0, 1], 'cam_R_w2c': list(np.eye(3).ravel()), 'cam_t_w2c': t}
+        with open(os.path.join(d, f'scene_camera_{cid}.json'), 'w') as fh:
+            json.dump({'0': entry(1.5, [1, 2, 3]), '7': entry(4.25 + c, [4, 5, 6.125])}, fh)
+        os.makedirs(os.path.join(d, f'rgb_{cid}'))
+        cv2.imwrite(os.path.join(d, f'rgb_{cid}', '000007.png'), np.full((8, 9, 3), 10 * c, np.uint8))
+    eye = list(np.eye(3).ravel())
+    with open(os.path.join(d, 'scene_gt_cam1.json'), 'w') as fh:
+        json.dump({'7': [{'obj_id': 8, 'cam_R_m2c': eye, 'cam_t_m2c': [1, 1, 1]}, {'obj_id': 9, 'cam_R_m2c': eye, 'cam_t_m2c': [2, 2, 2]}]}, fh)
+    with open(os.path.join(d, 'scene_gt_info_cam1.json'), 'w') as fh:
+        json.dump({'7': [{}, {}]}, fh)
+    p = load_camera_params(d, cams)
+    assert p['cam2']['K'][7].dtype == np.float32 and p['cam2']['K'][7].shape == (3, 3) and p['cam2']['K'][7][0, 0] == 5.25
+    assert p['cam3']['t'][0].shape == (3,) and p['cam1']['R'][0].dtype == np.float32
+    gt = load_gt_poses(d, '', cams, 7, 8)
+    assert len(gt) == 1 and gt[0].dtype == np.float64 and gt[0][0, 3] == 1
+    assert load_gt_poses(d, '', ['cam2'], 7, 8) == [] and load_gt_poses(d, '', cams, 3, 8) == []
+    cap = Capture.from_dir(d, cams, 7, 8)
+    assert [im.shape for im in cap.images] == [(8, 9, 3)] * 3 and int(cap.images[2][0, 0, 0]) == 20
+    assert all(k.dtype == np.float32 for k in cap.Ks) and all(rt.dtype == np.float64 and rt.shape == (4, 4) for rt in cap.RTs)
+    assert cap.RTs[1][2, 3] == 6.125 and cap.gt_poses.shape == (1, 4, 4)
