@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument('--cpu-scenes', type=int, default=256, help='scenes in the bounded CPU-baseline sample (~12 s on one core)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-crop-gather', action='store_true', help='skip the separate crop-gather stage at N > 1')
+    ap.add_argument('--gather-chunk', type=int, default=4096, help='uint8 crops per rank and chunk in the crop-gather stage')
+    ap.add_argument('--gather-steps', type=int, default=8)
     return ap.parse_args()
 
 
@@ -355,6 +358,40 @@ def main():
                        '(idx, n, cost, X) read back; crops stay in HBM for the on-device pose network '
                        '(the reference moves them H2D at process_pose.py:210)'}
 
+    # ---- crop gather to rank 0 (SURVEY.md 8e options 2/3), its own stage with its own bound: uint8 crops pulled
+    #      over NVLink by the receiver's normalise kernel; NOT part of `value` (crops stay sharded there) ----
+    crop_gather = None
+    if world > 1 and not args.no_crops and not args.no_crop_gather:
+        try:
+            gchunk = min(args.gather_chunk, n_rois)
+            cg = distributed.CropGather(gchunk, T=T, root=0, transport='p2p', device=dev)
+            g_rois = pipe.rois[:gchunk]
+            for i in range(3):
+                batched.roi_crop_u8(images, g_rois, T=T, out=cg.slot(i))
+                cg.collect(i)
+            torch.cuda.synchronize()
+            dist.barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            for i in range(args.gather_steps):
+                batched.roi_crop_u8(images, g_rois, T=T, out=cg.slot(i))
+                cg.collect(i)
+            g1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item()) * 1e-3 / args.gather_steps
+            crop_gather = {'transport': 'uint8 crops pulled over NVLink peer memory by the receiver kernel (bpc_crops_normalise)',
+                           'root': 0, 'chunk_rois_per_rank': gchunk, 'chunks': args.gather_steps,
+                           'crops_per_s': world * gchunk / sec, 'ms_per_chunk': sec * 1e3,
+                           'nvlink_ingest_GBps': cg.wire_bytes() / sec / 1e9, 'nvlink_peak_GBps': 900.0,
+                           'root_hbm_write_GBps': world * gchunk * 3 * T * T * 4 / sec / 1e9,
+                           'note': 'every rank produces a chunk of uint8 crops, rank 0 converts all of them to the float32 '
+                                   'network input; separate from `value`, where crops stay on the GPU that produced them'}
+            cg.close()
+        except Exception as exc:              # noqa: BLE001 -- the headline numbers do not depend on this stage
+            crop_gather = {'unavailable': f'{type(exc).__name__}: {exc}'[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -392,6 +429,8 @@ def main():
         'geometry_ms_per_step': match_ms / args.steps, 'crop_ms_per_step': crop_ms / args.steps,
         'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
     }
+    if crop_gather is not None:
+        line['crop_gather'] = crop_gather
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

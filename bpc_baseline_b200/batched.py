@@ -334,3 +334,36 @@ def roi_crop_u8(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(25
                                                    f, _p(out[lo:lo + r]), _p(status[lo:lo + r]) if status is not None else None,
                                                    _p(ws), ws.numel(), _stream(dev)), 'bpc_roi_crop_u8')
     return out
+
+
+def crops_normalise(sources: Sequence[torch.Tensor], T: int, swap_rb: bool = True, lut: Optional[torch.Tensor] = None,
+                    out: Optional[torch.Tensor] = None, device=None) -> torch.Tensor:
+    """uint8 letterboxed crops -> f32 [sum(n_s),3,T,T]: BGR2RGB + to_tensor + normalize (process_pose.py:206-209).
+
+    ``sources`` are uint8 [n_s,T,T,3] tensors (the output of :func:`roi_crop_u8`), concatenated in order.  They may
+    alias PEER memory (another rank's buffer obtained through ``distributed.PeerBuffers``); the kernel then pulls
+    the bytes over NVLink while it converts.  Bit-identical to :func:`roi_crop` on the same ROIs.
+    """
+    if not 1 <= len(sources) <= 16:
+        raise RuntimeError('1..16 sources')
+    for s in sources:
+        _chk(s, torch.uint8, 'sources[*]', 4)
+        if tuple(s.shape[1:]) != (T, T, 3):
+            raise RuntimeError('every source must be uint8 [n,T,T,3]')
+    dev = torch.device(device) if device is not None else sources[0].device
+    if lut is None:
+        lut = normalise_lut(dev)
+    _chk(lut, torch.float32, 'lut', 2)
+    total = sum(int(s.shape[0]) for s in sources)
+    if out is None:
+        out = torch.empty((total, 3, T, T), dtype=torch.float32, device=dev)
+    else:
+        _chk(out, torch.float32, 'out', 4)
+        if out.shape[0] < total or tuple(out.shape[1:]) != (3, T, T):
+            raise RuntimeError('out must be [>=sum(n_s),3,T,T]')
+    ptrs = (C.c_void_p * len(sources))(*[s.data_ptr() if s.shape[0] else None for s in sources])
+    counts = (C.c_int32 * len(sources))(*[int(s.shape[0]) for s in sources])
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().bpc_crops_normalise(ptrs, counts, len(sources), int(T), int(bool(swap_rb)), _p(lut), _p(out),
+                                                   _stream(dev)), 'bpc_crops_normalise')
+    return out

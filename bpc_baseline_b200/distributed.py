@@ -65,3 +65,118 @@ def gather_records(rec: torch.Tensor, group: Optional[dist.ProcessGroup] = None)
         for r, p in enumerate(parts):
             out[r] = p
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Crop gather (options 2 and 3).  float32 crops are 602 KB each and one GPU ingests at most
+# ~0.9 TB/s over NVLink 5, so the crops cross the wire as the uint8 letterboxed images (147 KB, bpc_roi_crop_u8)
+# and the BGR2RGB + to_tensor + normalize tail (process_pose.py:206-209) runs on the receiver.  Two transports:
+#   'p2p'  -- the receiver's normalise kernel reads every rank's uint8 buffer directly through peer-mapped
+#             pointers: transfer and conversion are ONE kernel, nothing is staged in the receiver's HBM;
+#   'nccl' -- dist.gather of the uint8 buffers into a staging area on the receiver, then the same kernel locally.
+# ------------------------------------------------------------------------------------------------------------
+class PeerBuffers:
+    """One uint8 buffer of ``nbytes`` per rank, each mapped into every process of the group (one node, NVLink).
+
+    ``local`` is this rank's buffer; ``views[r]`` aliases rank r's buffer (``views[rank] is local``).  The
+    mapping is torch's symmetric memory (CUDA VMM allocations whose handles are exchanged at the rendezvous and
+    mapped with access for the local device), so a kernel on this GPU can dereference ``views[r].data_ptr()``.
+    Collective: every rank of the group must construct it.
+    """
+
+    method = 'symm_mem'
+
+    def __init__(self, nbytes: int, device=None, group: Optional[dist.ProcessGroup] = None):
+        import torch.distributed._symmetric_memory as symm
+        if not dist.is_initialized():
+            raise RuntimeError('PeerBuffers needs an initialised process group')
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
+        self.nbytes = int(nbytes)
+        self.local = symm.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+        self._handle = symm.rendezvous(self.local, group=group if group is not None else dist.group.WORLD)
+        self.views = [self.local if r == self.rank else self._handle.get_buffer(r, (self.nbytes,), torch.uint8)
+                      for r in range(self.world)]
+
+    def close(self):
+        """Drop the peer mappings (collective: every rank must call it before the buffers are freed)."""
+        self.views = []
+        self._handle = None
+        if dist.is_initialized():
+            dist.barrier(group=self.group)
+
+
+class CropGather:
+    """Gathers the crops of every rank onto ``root`` as the float32 network input, chunk by chunk.
+
+    Every rank writes the uint8 crops of chunk i into ``slot(i)`` ([chunk_rois,T,T,3], double buffered) with
+    ``batched.roi_crop_u8`` and then calls ``collect(i, counts)``; on ``root`` this returns float32
+    [sum(counts),3,T,T] (a view of a reusable buffer), elsewhere None.  ``counts[r]`` = valid crops of rank r in
+    this chunk (default: full chunks).  Ordering between ranks comes from one tiny stream-ordered all-reduce per
+    chunk: it completes on the receiver only after every producer has enqueued -- and therefore finished -- its crop
+    kernel, and a producer reuses slot(i) at chunk i+2, after the all-reduce of chunk i+1, which the receiver
+    joins only after it has read chunk i.
+    """
+
+    def __init__(self, chunk_rois: int, T: int = 224, root: int = 0, transport: str = 'p2p', swap_rb: bool = True,
+                 device=None, group: Optional[dist.ProcessGroup] = None):
+        from . import batched
+        self._batched = batched
+        self.group, self.root, self.T, self.chunk = group, int(root), int(T), int(chunk_rois)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device(device if device is not None else f'cuda:{torch.cuda.current_device()}')
+        self.swap_rb = swap_rb
+        self.crop_bytes = self.T * self.T * 3
+        if transport not in ('p2p', 'nccl'):
+            raise ValueError("transport must be 'p2p' or 'nccl'")
+        self.transport = transport
+        shape = (self.chunk, self.T, self.T, 3)
+        if transport == 'p2p':
+            self.peers = PeerBuffers(2 * self.chunk * self.crop_bytes, device=self.device, group=group)
+            self._slots = [[v[b * self.chunk * self.crop_bytes:(b + 1) * self.chunk * self.crop_bytes].view(shape)
+                            for v in self.peers.views] for b in range(2)]
+        else:
+            self.peers = None
+            self._slots = [[torch.empty(shape, dtype=torch.uint8, device=self.device)] for _ in range(2)]
+            self._staging = (torch.empty((self.world,) + shape, dtype=torch.uint8, device=self.device)
+                             if self.rank == self.root else None)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.out = (torch.empty((self.world * self.chunk, 3, self.T, self.T), dtype=torch.float32, device=self.device)
+                    if self.rank == self.root else None)
+        self.lut = batched.normalise_lut(self.device)
+
+    def slot(self, i: int) -> torch.Tensor:
+        """This rank's uint8 [chunk_rois,T,T,3] buffer for chunk i."""
+        views = self._slots[i & 1]
+        return views[self.rank] if self.transport == 'p2p' else views[0]
+
+    def collect(self, i: int, counts=None):
+        counts = [self.chunk] * self.world if counts is None else [int(c) for c in counts]
+        if len(counts) != self.world or any(not 0 <= c <= self.chunk for c in counts):
+            raise ValueError('counts must hold one value in [0, chunk_rois] per rank')
+        if self.transport == 'p2p':
+            dist.all_reduce(self._flag, group=self.group)              # stream-ordered rendezvous, 4 bytes
+            if self.rank != self.root:
+                return None
+            srcs = [self._slots[i & 1][r][:counts[r]] for r in range(self.world)]
+        else:
+            mine = self.slot(i)
+            if self.rank == self.root:
+                dist.gather(mine, list(self._staging.unbind(0)), dst=self.root, group=self.group)
+                srcs = [self._staging[r, :counts[r]] for r in range(self.world)]
+            else:
+                dist.gather(mine, None, dst=self.root, group=self.group)
+                return None
+        return self._batched.crops_normalise(srcs, self.T, swap_rb=self.swap_rb, lut=self.lut, out=self.out,
+                                             device=self.device)[:sum(counts)]
+
+    def wire_bytes(self, counts=None) -> int:
+        """Bytes that cross NVLink into the root for one chunk (the root's own crops do not travel)."""
+        counts = [self.chunk] * self.world if counts is None else counts
+        return int(sum(c for r, c in enumerate(counts) if r != self.root) * self.crop_bytes)
+
+    def close(self):
+        self._slots = []
+        if self.peers is not None:
+            self.peers.close()

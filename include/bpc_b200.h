@@ -192,6 +192,19 @@ int bpc_roi_crop_u8(const uint8_t* images, int B, int H, int W, const int32_t* r
  * to_tensor (.div(255)) + normalize (.sub_(mean).div_(std)); process_pose.py:207-209. */
 int bpc_normalise_lut(const float* mean_host3, const float* std_host3, float* lut, void* stream);
 
+/* ---- crop gather (receiver side) --------------------------------------------------------------
+ * The colour swap + to_tensor + normalize tail of process_pose.py:206-209 applied to uint8
+ * letterboxed crops [count][T][T][3] (the output of bpc_roi_crop_u8) that live in up to 16 source
+ * buffers, concatenated in source order into out float32 [sum(counts)][3][T][T]; bit-identical to
+ * what bpc_roi_crop writes for the same ROIs.  `srcs` and `counts` are HOST arrays of n_src device
+ * pointers / crop counts.  A source pointer may be another GPU's buffer mapped into this process
+ * (e.g. torch symmetric memory: a VMM mapping with access for this device): the
+ * kernel then pulls the bytes over NVLink while converting -- the gather and the arithmetic are one
+ * kernel and the wire carries 1 byte per sample instead of 4.  Fast path: T % 4 == 0 and 16-byte
+ * aligned pointers; anything else takes a scalar kernel. */
+int bpc_crops_normalise(const uint8_t* const* srcs, const int32_t* counts, int n_src, int T, int swap_rb,
+                        const float* lut, float* out, void* stream);
+
 /* Number of kernel launches issued by this library since load (all entry points). */
 unsigned long long bpc_launch_count(void);
 
