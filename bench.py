@@ -60,10 +60,13 @@ def parse_args():
 
 
 def workload_config(args):
+    name = ('config 2' if (args.scenes, args.dets) == (4096, 20) and not args.no_crops
+            else 'config 3 (dense bin)' if args.dets == 200 else 'custom')
+    path = ('geometry only (no crops)' if args.no_crops else
+            f'full path incl. {args.target}x{args.target} float32 crops of every matched detection in 3 views')
     return {
-        'workload': f'config 2: {args.scenes} synthetic 3-camera scenes x {args.dets} detections per GPU per step '
-                    f'(sigma={args.sigma}px, p_drop={args.p_drop}); full path incl. {args.target}x{args.target} '
-                    f'float32 crops of every matched detection in 3 views',
+        'workload': f'{name}: {args.scenes} synthetic 3-camera scenes x {args.dets} detections per GPU per step '
+                    f'(sigma={args.sigma}px, p_drop={args.p_drop}); {path}',
         'scenes_per_gpu': args.scenes, 'detections_per_camera': args.dets, 'target_size': args.target,
         'image_pool': f'{args.pool} triplets of 3840x2160 BGR uint8 ({args.pool * 3 * 3840 * 2160 * 3 / 1e6:.0f} MB), '
                       'scene s uses triplet s % pool',
