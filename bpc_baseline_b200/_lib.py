@@ -33,6 +33,7 @@ SIGNATURES = {
     'bpc_box_centers': (_i, [_p, _i, _p, _p]),
     'bpc_detections_from_yolo': (_i, [_p, _p, _p, _p, _i, _i, _f, _i, _p, _p, _p, _p]),
     'bpc_build_rois': (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
+    'bpc_train_rois': (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p]),
     'bpc_roi_crop_workspace_bytes': (_sz, [_i]),
     'bpc_roi_crop': (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
     'bpc_roi_crop_u8': (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),

@@ -367,3 +367,30 @@ def crops_normalise(sources: Sequence[torch.Tensor], T: int, swap_rb: bool = Tru
         _lib.check(_lib.load().bpc_crops_normalise(ptrs, counts, len(sources), int(T), int(bool(swap_rb)), _p(lut), _p(out),
                                                    _stream(dev)), 'bpc_crops_normalise')
     return out
+
+
+def train_rois(xywh: torch.Tensor, W: int, H: int, image: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None,
+               shift: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ROI records i32 [n,5] of the dataset's crops (data_utils.py:243-271): the original window, or with ``scale``
+    (f64 [n]) / ``shift`` (i32 [n,2]) the jittered one.  Feed to :func:`roi_crop` with ``swap_rb=False``."""
+    _chk(xywh, torch.int32, 'xywh', 2)
+    n = xywh.shape[0]
+    if xywh.shape[1] != 4:
+        raise RuntimeError('xywh must be [n,4]')
+    if image is not None:
+        _chk(image, torch.int32, 'image', 1)
+    if scale is not None:
+        _chk(scale, torch.float64, 'scale', 1)
+    if shift is not None:
+        _chk(shift, torch.int32, 'shift', 2)
+        if scale is None:
+            raise RuntimeError('shift needs scale (the reference draws both, data_utils.py:257-263)')
+    for t, name in ((image, 'image'), (scale, 'scale'), (shift, 'shift')):
+        if t is not None and t.shape[0] != n:
+            raise RuntimeError(f'{name}: first dimension must be {n}')
+    dev = xywh.device
+    rois = torch.empty((n, 5), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().bpc_train_rois(_p(xywh), _p(image), _p(scale), _p(shift), n, int(W), int(H), _p(rois),
+                                              _stream(dev)), 'bpc_train_rois')
+    return rois

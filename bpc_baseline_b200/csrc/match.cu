@@ -766,3 +766,44 @@ extern "C" int bpc_build_rois(const int32_t* boxes, const int32_t* idx, const in
     BPC_LAUNCH_CHECK();
     return BPC_OK;
 }
+
+// ---- training-side ROI records: BOPSingleObjDataset.__getitem__, bpc/utils/data_utils.py:243-271 ----
+// bbox_visib (x, y, w, h) -> the crop the dataset takes, with the scale / shift jitter of :257-271 when a draw
+// is supplied (scale = 1.0 + 0.2 * random.random(), shift_x/y = random.randint(-int(0.1 w), int(0.1 w)) ...;
+// the draws themselves stay on the host so that Python's `random` stream is the reference's).
+namespace bpc {
+__global__ void bpc_train_rois_kernel(const int32_t* __restrict__ xywh, const int32_t* __restrict__ image,
+                                      const double* __restrict__ scale, const int32_t* __restrict__ shift, int n, int W, int H,
+                                      int32_t* __restrict__ rois) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    const int x = xywh[4 * r], y = xywh[4 * r + 1], w = xywh[4 * r + 2], h = xywh[4 * r + 3];
+    int x1, y1, x2, y2;
+    if (scale) {
+        // int(round(w * s)): Python round() of the float64 product = round-half-even (:258-259)
+        int aw = (int)rint(dmul((double)w, scale[r]));
+        int ah = (int)rint(dmul((double)h, scale[r]));
+        const int sx = shift ? shift[2 * r] : 0, sy = shift ? shift[2 * r + 1] : 0;
+        x1 = max(0, min(x - sx, W - 1));                      // :264-265
+        y1 = max(0, min(y - sy, H - 1));
+        aw = min(aw, W - x1);                                 // :266-267
+        ah = min(ah, H - y1);
+        x2 = x1 + aw; y2 = y1 + ah;
+    } else {
+        // bgr[y:y+h, x:x+w] (:246): NumPy clamps the slice ends to the image; starts are taken as given
+        x1 = x; y1 = y; x2 = min(x + w, W); y2 = min(y + h, H);
+    }
+    int32_t* o = rois + 5 * (size_t)r;
+    o[0] = image ? image[r] : 0; o[1] = x1; o[2] = y1; o[3] = x2; o[4] = y2;
+}
+}  // namespace bpc
+
+extern "C" int bpc_train_rois(const int32_t* xywh, const int32_t* image, const double* scale, const int32_t* shift, int n,
+                              int W, int H, int32_t* rois, void* stream) {
+    if (n < 0 || W < 1 || H < 1) return BPC_EINVAL;
+    if (n == 0) return BPC_OK;
+    if (!xywh || !rois || (shift && !scale)) return BPC_EINVAL;
+    bpc::bpc_train_rois_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(xywh, image, scale, shift, n, W, H, rois);
+    BPC_LAUNCH_CHECK();
+    return BPC_OK;
+}

@@ -101,3 +101,48 @@ class Capture:
             hits = glob.glob(os.path.join(scene_dir, f"rgb_{c}", f"{image_id:06d}.*g"))
             images.append(cv2.imread(hits[0]))
         return cls(images, Ks, RTs, obj_id, load_gt_poses(scene_dir, '', cam_ids, image_id, obj_id))
+
+
+def draw_crop_jitter(bbox_visib, rnd=None):
+    """The three draws BOPSingleObjDataset.__getitem__ makes per sample, in its order (data_utils.py:257-263):
+    ``scale_factor = 1.0 + 0.2 * random.random()``, then ``randint`` for shift_x and shift_y within +-int(0.1 * side).
+    ``rnd`` defaults to Python's global ``random`` module, so seeding it reproduces the reference's boxes.
+    Returns (scale float64 [n], shift int32 [n, 2])."""
+    import random
+    rnd = random if rnd is None else rnd
+    boxes = np.asarray(bbox_visib).reshape(-1, 4)
+    scale = np.empty(len(boxes), np.float64)
+    shift = np.empty((len(boxes), 2), np.int32)
+    for r, (_, _, w, h) in enumerate(boxes):
+        scale[r] = 1.0 + 0.2 * rnd.random()
+        max_x, max_y = int(0.1 * int(w)), int(0.1 * int(h))
+        shift[r] = (rnd.randint(-max_x, max_x), rnd.randint(-max_y, max_y))
+    return scale, shift
+
+
+def dataset_crops(images, bbox_visib, image_index=None, target_size=256, jitter=None, as_uint8=False):
+    """Batched crop transform of BOPSingleObjDataset.__getitem__ (data_utils.py:243-252, 282; jittered window :257-271).
+
+    ``images`` uint8 [B, H, W, 3] BGR (NumPy or CUDA tensor), ``bbox_visib`` int [n, 4] = (x, y, w, h), ``jitter`` =
+    None for the original crop or the (scale, shift) pair of :func:`draw_crop_jitter` for the augmented window.
+    Returns the normalised float32 [n, 3, T, T] CUDA tensor in the dataset's channel order (BGR kept, no swap), or the
+    uint8 letterboxed images [n, T, T, 3] with ``as_uint8`` (what the reference hands to ColorJitter, which is not
+    built here).  Raises RuntimeError on an empty crop, as the reference (:247-248, :269-270).
+    """
+    import torch
+    imgs = images if isinstance(images, torch.Tensor) else _host.to_dev(images, np.uint8)
+    _, H, W, _ = imgs.shape
+    xywh = _host.to_dev(np.asarray(bbox_visib).reshape(-1, 4), np.int32)
+    idx = None if image_index is None else _host.to_dev(image_index, np.int32)
+    scale = shift = None
+    if jitter is not None:
+        scale, shift = _host.to_dev(jitter[0], np.float64), _host.to_dev(jitter[1], np.int32)
+    rois = batched.train_rois(xywh, W, H, image=idx, scale=scale, shift=shift)
+    status = torch.zeros(rois.shape[0], dtype=torch.int32, device=rois.device)
+    if as_uint8:
+        out = batched.roi_crop_u8(imgs, rois, T=int(target_size), status=status)
+    else:
+        out = batched.roi_crop(imgs, rois, T=int(target_size), swap_rb=False, status=status)
+    if int(status.sum().item()):
+        raise RuntimeError('Empty crop for %s image' % ('augmented' if jitter is not None else 'original'))
+    return out

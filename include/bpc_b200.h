@@ -157,6 +157,21 @@ int bpc_build_rois(const int32_t* boxes, const int32_t* idx, const int32_t* n, c
                    int S, int Dmax, int Kmax, int32_t* scene_offset, int32_t* rois, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training-side ROI records: the crop windows BOPSingleObjDataset.__getitem__
+ * takes, bpc/utils/data_utils.py:243-271, as rois int32 [n][5] for bpc_roi_crop (swap_rb = 0: the
+ * dataset keeps the BGR order, :249-252).
+ *   xywh   int32 [n][4]   bbox_visib (x, y, w, h)                               :242
+ *   image  int32 [n]      index of each sample's image in the pool; NULL = 0
+ *   scale  double [n]     NULL = the original crop bgr[y:y+h, x:x+w] (:246); else the augmented one:
+ *                         scale_factor of :257, aug_w = int(round(w * scale)) (half-to-even), clamps of :264-267
+ *   shift  int32 [n][2]   (shift_x, shift_y) of :262-263; NULL = 0.  The random draws stay on the host
+ *                         (Python's `random` stream is the reference's); this only applies them.
+ *   W, H   image size
+ */
+int bpc_train_rois(const int32_t* xywh, const int32_t* image, const double* scale, const int32_t* shift, int n,
+                   int W, int H, int32_t* rois, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * a11 + a12. Crop -> letterbox (INTER_AREA) -> colour order -> /255 -> normalise, for R ROIs.
  * Replaces letterbox_preserving_aspect_ratio, bpc/utils/data_utils.py:34-44, and the inline
  * transform of PoseEstimator._estimate_rotation, bpc/inference/process_pose.py:199-209

@@ -99,3 +99,23 @@ def crops_ref(images, rois, target_size=256, swap_rb=True):
     for r, (b, x1, y1, x2, y2) in enumerate(np.asarray(rois)):
         out[r] = crop_tensor_ref(images[b], (x1, y1, x2, y2), target_size, swap_rb)
     return out
+
+
+def dataset_window(bbox_visib, W, H, scale=None, shift=(0, 0)):
+    """Crop window (x1, y1, x2, y2) of BOPSingleObjDataset.__getitem__ -- data_utils.py:242-246 (original,
+    scale=None) and :257-268 (augmented, given the draws scale_factor and (shift_x, shift_y))."""
+    x, y, w, h = (int(v) for v in bbox_visib)
+    if scale is None:
+        return x, y, min(x + w, W), min(y + h, H)              # NumPy slicing clamps the ends
+    aug_w = int(round(w * float(scale)))
+    aug_h = int(round(h * float(scale)))
+    aug_x = max(0, min(x - int(shift[0]), W - 1))
+    aug_y = max(0, min(y - int(shift[1]), H - 1))
+    aug_w = min(aug_w, W - aug_x)
+    aug_h = min(aug_h, H - aug_y)
+    return aug_x, aug_y, aug_x + aug_w, aug_y + aug_h
+
+
+def dataset_tensor_ref(image, window, target_size=256):
+    """orig_img_t of the dataset: letterbox, HWC->CHW, /255, normalize -- BGR order kept (data_utils.py:249-252, 282)."""
+    return crop_tensor_ref(image, window, target_size=target_size, swap_rb=False)

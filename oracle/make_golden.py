@@ -205,15 +205,88 @@ def golden_crops(ref):
     print(f'  crops: {len(boxes)} boxes x T in (224, 64), every other box at T=256')
 
 
+def golden_dataset(ref):
+    """train_crops.npz: BOPSingleObjDataset.__getitem__ (data_utils.py:233-298) on a temp train_pbr directory.
+
+    Recorded per sample: bbox_visib, the three jitter draws (re-drawn from the same seed by the same calls), and --
+    through a pass-through recorder around the reference's letterbox_preserving_aspect_ratio -- the shape of the
+    window the dataset actually cropped and the uint8 canvas it got back, for the original and the augmented crop;
+    plus orig_img_t (float32) for a few samples.  The augmented tensor itself goes through ColorJitter (torch RNG,
+    PIL arithmetic) and is not recorded.
+    """
+    import random
+    import cv2
+    from bpc_baseline_b200 import synth
+    H, W, T, obj = 540, 720, 64, 8
+    image = synth.make_images(1, seed=synth.SEED + 11, width=W, height=H)[0]
+    rng = np.random.default_rng([synth.SEED, 11])
+    boxes = []
+    for _ in range(10):
+        w, h = (int(v) for v in rng.integers(40, 300, 2))
+        boxes.append([int(rng.integers(0, W - w + 1)), int(rng.integers(0, H - h + 1)), w, h])
+    boxes += [[W - 120, H - 90, 120, 90], [0, 0, 200, 150], [W - 61, 10, 60, 200], [3, H - 75, 333, 70],   # clamps fire
+              [100, 100, 250, 250], [0, 200, 45, 37]]
+    with tempfile.TemporaryDirectory() as root:
+        scene = os.path.join(root, 'train_pbr', '000000')
+        os.makedirs(os.path.join(scene, 'rgb_cam1'))
+        cv2.imwrite(os.path.join(scene, 'rgb_cam1', '000000.png'), image)
+        ident = [1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0]
+        info = {'0': [{'bbox_visib': b, 'visib_fract': 1.0, 'px_count_all': 5000, 'px_count_valid': 5000} for b in boxes]}
+        gt = {'0': [{'obj_id': obj, 'cam_R_m2c': ident, 'cam_t_m2c': [0.0, 0.0, 1000.0]} for _ in boxes]}
+        cam = {'0': {'cam_K': [1000.0, 0.0, 360.0, 0.0, 1000.0, 270.0, 0.0, 0.0, 1.0], 'depth_scale': 1.0}}
+        for name, blob in (('scene_gt_info_cam1', info), ('scene_gt_cam1', gt), ('scene_camera_cam1', cam)):
+            with open(os.path.join(scene, name + '.json'), 'w') as fh:
+                json.dump(blob, fh)
+        ds = quiet(ref.du.BOPSingleObjDataset, root, ['000000'], ['cam1'], obj, target_size=T, augment=True,
+                   split='train', train_ratio=1.0)
+        assert len(ds) == len(boxes)
+        calls = []
+        real = ref.du.letterbox_preserving_aspect_ratio
+
+        def recorder(img, target_size=256, fill_color=(255, 255, 255)):
+            out = real(img, target_size=target_size, fill_color=fill_color)
+            calls.append((img.shape[:2], out[0].copy()))
+            return out
+
+        ref.du.letterbox_preserving_aspect_ratio = recorder
+        try:
+            rec = {k: [] for k in ('bbox', 'scale', 'shift', 'orig_hw', 'aug_hw', 'orig_canvas', 'aug_canvas', 'orig_t')}
+            for i in range(len(ds)):
+                x, y, w, h = ds.samples[i]['bbox_visib']
+                random.seed(1000 + i)
+                scale = 1.0 + 0.2 * random.random()                # the same three calls as data_utils.py:257-263
+                shift = (random.randint(-int(0.1 * w), int(0.1 * w)), random.randint(-int(0.1 * h), int(0.1 * h)))
+                random.seed(1000 + i)
+                del calls[:]
+                orig_t, _aug_t, _labels, _meta = ds[i]
+                assert len(calls) == 2
+                rec['bbox'].append([x, y, w, h]); rec['scale'].append(scale); rec['shift'].append(shift)
+                rec['orig_hw'].append(calls[0][0]); rec['aug_hw'].append(calls[1][0])
+                rec['orig_canvas'].append(calls[0][1]); rec['aug_canvas'].append(calls[1][1])
+                if i < 4:
+                    rec['orig_t'].append(orig_t.numpy())
+        finally:
+            ref.du.letterbox_preserving_aspect_ratio = real
+    np.savez_compressed(os.path.join(GOLDEN, 'train_crops.npz'), image=image, T=np.int32(T),
+                        bbox=np.array(rec['bbox'], np.int32), scale=np.array(rec['scale'], np.float64),
+                        shift=np.array(rec['shift'], np.int32), orig_hw=np.array(rec['orig_hw'], np.int32),
+                        aug_hw=np.array(rec['aug_hw'], np.int32), orig_canvas=np.stack(rec['orig_canvas']),
+                        aug_canvas=np.stack(rec['aug_canvas']), orig_t=np.stack(rec['orig_t']))
+    print(f'  dataset: {len(boxes)} samples at T={T} (order after the constructor shuffle)')
+
+
 def main():
     if not os.path.isdir(REFERENCE):
         raise SystemExit('needs /root/reference (authoring container only)')
     sys.path.insert(0, ROOT)
     os.makedirs(GOLDEN, exist_ok=True)
     ref = import_reference()
-    print('geometry'); golden_geometry(ref)
-    print('bop scene'); golden_bop_scene(ref)
-    print('crops'); golden_crops(ref)
+    only = set(sys.argv[1:])
+    for name, fn in (('geometry', golden_geometry), ('bop_scene', golden_bop_scene), ('crops', golden_crops),
+                     ('dataset', golden_dataset)):
+        if not only or name in only:
+            print(name)
+            fn(ref)
 
 
 if __name__ == '__main__':

@@ -63,3 +63,8 @@ def golden_crops():
 @pytest.fixture(scope='session')
 def golden_bop():
     return np.load(os.path.join(GOLDEN, 'bop_scene.npz'))
+
+
+@pytest.fixture(scope='session')
+def golden_train():
+    return np.load(os.path.join(GOLDEN, 'train_crops.npz'))
