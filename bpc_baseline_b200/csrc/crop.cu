@@ -24,6 +24,8 @@
 //                     streamed through shared memory in chunks (handles boxes as large as the image).
 // The dominant traffic is the float32 output (3*T*T*4 B per ROI): each warp stores 128 contiguous bytes per
 // plane and row; padding rows are written with 16-byte stores.
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace bpc {
@@ -182,7 +184,8 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                         const int seg_px = (int)(31.0 * g.scale_x) + (int)ceil(g.scale_x) + 3;
                         const int pitch_max = ((3 * seg_px + 46) >> 4) << 4;
                         const int rows_need = (int)ceil(g.scale_y) + 4;
-                        g.cls = (pitch_max <= 512 && WARP_BUF / pitch_max >= rows_need) ? 4 : 2;
+                        const bool taps6 = (int)ceil(g.scale_x) + 1 <= 6 && (int)ceil(g.scale_y) + 1 <= 6;
+                        g.cls = (taps6 && pitch_max <= 512 && WARP_BUF / pitch_max >= rows_need) ? 4 : 2;
                     } else g.cls = 2;
                 }
             }
@@ -359,6 +362,30 @@ __device__ __forceinline__ void h_area3(unsigned a4, int sh, const ColW& cw, u64
     const float r2 = __fmaf_rn(magic_byte<0>(v2), cw.w[2], cw.c[2]);
     h01 = fadd2(fadd2(p0, p1), p2);
     h2 = __fadd_rn(__fadd_rn(r0, r1), r2);
+}
+
+// horizontal pass with NT taps evaluated (4..6): 3*NT bytes starting at shared address a4 + sh/8.  Taps beyond a
+// lane's own count carry weight +0.0f (c = -0.0f): fma(2^23 + b, +0, -0) = +0 and s + (+0) = s, so padding the
+// tap list to the warp's maximum leaves every sum bit-identical to the sequential ((S0*w0 + S1*w1) + ...) order.
+template <int NT>
+__device__ __forceinline__ void h_area_n(unsigned a4, int sh, const float (&w)[6], const float (&c)[6], u64& h01, float& h2) {
+    constexpr int NV = (3 * NT + 3) / 4;            // aligned words holding 3*NT bytes; NV + 1 raw words cover any shift
+    unsigned q[NV + 1], v[NV];
+#pragma unroll
+    for (int i = 0; i <= NV; ++i) q[i] = lds_u32(a4 + 4 * i);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = __funnelshift_r(q[i], q[i + 1], sh);
+#pragma unroll
+    for (int k = 0; k < NT; ++k) {
+        const int j = 3 * k;
+        const float b0 = __uint_as_float(__byte_perm(v[j >> 2], 0x4B000000u, 0x7540 + (j & 3)));
+        const float b1 = __uint_as_float(__byte_perm(v[(j + 1) >> 2], 0x4B000000u, 0x7540 + ((j + 1) & 3)));
+        const float b2 = __uint_as_float(__byte_perm(v[(j + 2) >> 2], 0x4B000000u, 0x7540 + ((j + 2) & 3)));
+        const u64 p = ffma2(pack2(b0, b1), pack2(w[k], w[k]), pack2(c[k], c[k]));
+        const float r = __fmaf_rn(b2, w[k], c[k]);
+        h01 = (k == 0) ? p : fadd2(h01, p);
+        h2 = (k == 0) ? r : __fadd_rn(h2, r);
+    }
 }
 
 // horizontal pass of the fixed-point bilinear: 6 bytes at shared address a4 + sh/8, result pre-shifted by 4
@@ -561,72 +588,81 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
         int s_lo_next = 0;
 
         if (cls == 4) {
-            // ---------------- regime 1, any tap count (scale >= 2): scalar loops over the taps ----------------
-            const float w0 = xd.x, wm = xd.y, wl = xd.z;
-            const float c0 = __fmul_rn(w0, -8388608.0f), cm = __fmul_rn(wm, -8388608.0f), cl = __fmul_rn(wl, -8388608.0f);
-            int crow = -1;
-            float hc[3] = {0.f, 0.f, 0.f};
-            auto hrow = [&](unsigned rowaddr, float* h) {      // sequential taps: ((S0*w0 + S1*wm) + ...) + Sl*wl
+            // ---------------- regime 1, up to 6 taps per axis (2 <= scale <~ 4.2): taps padded to the warp maximum ----------------
+            const int nt = warp_max_i32(xn);                      // uniform: taps evaluated per source row
+            float w[6], c[6];
 #pragma unroll
-                for (int c = 0; c < 3; ++c) h[c] = __fmaf_rn(__uint_as_float(lds_u8(rowaddr + c) + 0x4B000000u), w0, c0);
-                for (int k = 1; k < xn - 1; ++k)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        h[c] = __fadd_rn(h[c], __fmaf_rn(__uint_as_float(lds_u8(rowaddr + 3 * k + c) + 0x4B000000u), wm, cm));
-                if (xn > 1)
-#pragma unroll
-                    for (int c = 0; c < 3; ++c)
-                        h[c] = __fadd_rn(h[c], __fmaf_rn(__uint_as_float(lds_u8(rowaddr + 3 * (xn - 1) + c) + 0x4B000000u), wl, cl));
-            };
-            for (int b = 0; b < nb; ++b) {
-                const int k = b & 1;
-                if (bulk_cur) {
-                    if (k == 0) { mbar_wait(bar_s, phase0); phase0 ^= 1u; } else { mbar_wait(bar_s + 8, phase1); phase1 ^= 1u; }
-                } else {
-                    cp_async_wait_all();
-                }
-                __syncwarp();
-                if (b + 1 < nb) s_lo_next = stage(b + 1, k ^ 1, ydn);
-                ydn = load_desc(b + 2);
-                const unsigned cur = wbase_s + k * WARP_BUF, ring = wbase_s + 2 * WARP_BUF + k * WARP_DESC;
-                const int y0 = b * bh, cnt = min(bh, new_h - y0);
-                if (active) {
-                    for (int r = 0; r < cnt; ++r) {
-                        const float4 d = lds_f4(ring + r * 16);
-                        const int ysn = __float_as_int(d.w);
-                        const int ys = ysn & 0xffffff, n = ysn >> 24;
-                        float acc[3];
-                        for (int t = 0; t < n; ++t) {
-                            const int row = ys + t;
-                            if (row != crow) {
-                                int a = (row - s_lo_cur) * pitch + colc;
-                                if (!ALIGNED) a += (mis0 + row * misstep) & 15;
-                                hrow(cur + a, hc);
-                                crow = row;
-                            }
-                            const float beta = (t == 0) ? d.x : ((t == n - 1) ? d.z : d.y);
-#pragma unroll
-                            for (int c = 0; c < 3; ++c) {
-                                const float term = __fmul_rn(beta, hc[c]);
-                                acc[c] = (t == 0) ? term : __fadd_rn(acc[c], term);
-                            }
-                        }
-                        const int o0 = round_u8(acc[0]), o1 = round_u8(acc[1]), o2 = round_u8(acc[2]);
-                        if (OUT_U8) {
-                            out.px(roi, dy0 + y0 + r, x, o0, o1, o2);
-                        } else {
-                            optr[0] = lds_f32(lut_s + 4 * (swap ? o2 : o0));
-                            optr[plane] = lds_f32(lut_s + 1024 + 4 * o1);
-                            optr[2 * plane] = lds_f32(lut_s + 2048 + 4 * (swap ? o0 : o2));
-                            optr += T;
-                        }
-                    }
-                } else if (padlane) {
-                    for (int r = 0; r < cnt; ++r) out.pad(roi, dy0 + y0 + r, x);
-                }
-                s_lo_cur = s_lo_next;
-                bulk_cur = bulk_next;
+            for (int k = 0; k < 6; ++k) {
+                w[k] = (k == 0) ? xd.x : ((k < xn - 1) ? xd.y : ((k == xn - 1) ? xd.z : 0.f));
+                c[k] = __fmul_rn(w[k], -8388608.0f);
+                asm volatile("" : "+f"(c[k]));
             }
+            int crow = -1;
+            u64 hc01 = 0ull;
+            float hc2 = 0.f;
+            // the whole strip loop is instantiated per tap count so that the horizontal pass is straight-line code
+            auto strip = [&](auto nt_c) {
+                constexpr int NT = decltype(nt_c)::value;
+                for (int b = 0; b < nb; ++b) {
+                    const int k = b & 1;
+                    if (bulk_cur) {
+                        if (k == 0) { mbar_wait(bar_s, phase0); phase0 ^= 1u; } else { mbar_wait(bar_s + 8, phase1); phase1 ^= 1u; }
+                    } else {
+                        cp_async_wait_all();
+                    }
+                    __syncwarp();
+                    if (b + 1 < nb) s_lo_next = stage(b + 1, k ^ 1, ydn);
+                    ydn = load_desc(b + 2);
+                    const unsigned cur = wbase_s + k * WARP_BUF, ring = wbase_s + 2 * WARP_BUF + k * WARP_DESC;
+                    const int y0 = b * bh, cnt = min(bh, new_h - y0);
+                    if (active) {
+                        const unsigned abase = cur + colc4 - (unsigned)(s_lo_cur * pitch);     // ALIGNED: row r starts at abase + r * pitch
+                        auto hrow = [&](int row, unsigned a4) {
+                            if (ALIGNED) {
+                                h_area_n<NT>(a4, shc, w, c, hc01, hc2);
+                            } else {
+                                const int a = (row - s_lo_cur) * pitch + colc + ((mis0 + row * misstep) & 15);
+                                h_area_n<NT>(cur + (a & ~3), (a & 3) * 8, w, c, hc01, hc2);
+                            }
+                        };
+                        for (int r = 0; r < cnt; ++r) {
+                            const float4 d = lds_f4(ring + r * 16);
+                            const int ysn = __float_as_int(d.w);
+                            const int ys = ysn & 0xffffff, n = ysn >> 24;
+                            unsigned a4 = abase + (unsigned)(ys * pitch);
+                            if (ys != crow) hrow(ys, a4);            // else: the previous output row ended on this source row
+                            u64 acc01 = fprod2(pack2(d.x, d.x), hc01, nz2);
+                            float acc2 = __fmul_rn(d.x, hc2);
+                            for (int t = 1; t < n; ++t) {
+                                a4 += pitch;
+                                hrow(ys + t, a4);
+                                const float beta = (t == n - 1) ? d.z : d.y;
+                                acc01 = fadd2(acc01, fprod2(pack2(beta, beta), hc01, nz2));
+                                acc2 = __fadd_rn(acc2, __fmul_rn(beta, hc2));
+                            }
+                            crow = ys + n - 1;
+                            float a0f, a1f;
+                            unpack2(acc01, a0f, a1f);
+                            if (OUT_U8) {
+                                out.px(roi, dy0 + y0 + r, x, round_u8(a0f), round_u8(a1f), round_u8(acc2));
+                            } else {
+                                const unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
+                                optr[0] = lds_f32(swap ? l2 : l0);
+                                optr[plane] = lds_f32(l1 + 1024);
+                                optr[2 * plane] = lds_f32((swap ? l0 : l2) + 2048);
+                                optr += T;
+                            }
+                        }
+                    } else if (padlane) {
+                        for (int r = 0; r < cnt; ++r) out.pad(roi, dy0 + y0 + r, x);
+                    }
+                    s_lo_cur = s_lo_next;
+                    bulk_cur = bulk_next;
+                }
+            };
+            if (nt <= 4) strip(std::integral_constant<int, 4>{});
+            else if (nt == 5) strip(std::integral_constant<int, 5>{});
+            else strip(std::integral_constant<int, 6>{});
         } else if (cls == 1) {
             ColW cw;
             cw.set(xd.x, xd.y, xd.z);
