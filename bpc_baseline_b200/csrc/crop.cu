@@ -34,7 +34,7 @@ constexpr int CROP_BAND = 8;                 // generic kernel: output rows per 
 constexpr int CROP_RAW_BYTES = 40 * 1024;    // generic kernel: staged source bytes
 constexpr int WARP_BUF = 3584;               // warp kernel: bytes of one staging buffer (two per warp)
 constexpr int WARP_DESC = 32 * 16;           // warp kernel: 32 row descriptors (two rings per warp)
-constexpr int WARP_SMEM = 2 * WARP_BUF + 2 * WARP_DESC + 16;   // + two mbarriers
+constexpr int WARP_SMEM = 2 * WARP_BUF + 2 * WARP_DESC + 32;   // + four mbarriers (classes 1 / 3 use two)
 constexpr int WARPK_WARPS = 8;
 constexpr int WARPK_SMEM = WARPK_WARPS * WARP_SMEM + 768 * 4;
 constexpr int DESC_STRIDE = 256;             // descriptors per ROI and axis (T <= 256)
@@ -183,9 +183,8 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                         // 32 columns span at most 31*scale_x + ceil(scale_x) + 2 source pixels
                         const int seg_px = (int)(31.0 * g.scale_x) + (int)ceil(g.scale_x) + 3;
                         const int pitch_max = ((3 * seg_px + 46) >> 4) << 4;
-                        const int rows_need = (int)ceil(g.scale_y) + 4;
                         const bool taps6 = (int)ceil(g.scale_x) + 1 <= 6 && (int)ceil(g.scale_y) + 1 <= 6;
-                        g.cls = (taps6 && pitch_max <= 512 && WARP_BUF / pitch_max >= rows_need) ? 4 : 2;
+                        g.cls = (taps6 && 8 * pitch_max <= 2 * WARP_BUF) ? 4 : 2;      // ring slots of >= 2 rows
                     } else g.cls = 2;
                 }
             }
@@ -487,9 +486,9 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
     const unsigned wbase_s = (unsigned)__cvta_generic_to_shared(wbase), lut_s = (unsigned)__cvta_generic_to_shared(smem);
 
     const unsigned lut_m = lut_s - 4u * 0x4B000000u;                    // see lut_addr()
-    const unsigned bar_s = wbase_s + 2 * WARP_BUF + 2 * WARP_DESC;     // two mbarriers, one per staging buffer
-    if (lane == 0) { mbar_init(bar_s, 1); mbar_init(bar_s + 8, 1); }
-    unsigned phase0 = 0, phase1 = 0;                                      // parity of the next completion of each barrier
+    const unsigned bar_s = wbase_s + 2 * WARP_BUF + 2 * WARP_DESC;     // four mbarriers: one per staging buffer / ring slot
+    if (lane == 0) { mbar_init(bar_s, 1); mbar_init(bar_s + 8, 1); mbar_init(bar_s + 16, 1); mbar_init(bar_s + 24, 1); }
+    unsigned ph = 0;                                                      // bit j: parity of the next completion of barrier j
     if (!OUT_U8)
         for (int e = tid; e < 768; e += 256) lut[e] = lut_g[e];
     __syncthreads();
@@ -581,14 +580,11 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             return (b < nb && y < new_h && lane < bh) ? ydr[y] : zero4;
         };
 
-        __syncwarp();                                   // previous item finished with the buffers
-        int s_lo_cur = stage(0, 0, load_desc(0));
-        bulk_cur = bulk_next;
-        float4 ydn = load_desc(1);
-        int s_lo_next = 0;
-
         if (cls == 4) {
-            // ---------------- regime 1, up to 6 taps per axis (2 <= scale <~ 4.2): taps padded to the warp maximum ----------------
+            // ---------------- regime 1, up to 6 taps per axis (2 <= scale <= 5) ----------------
+            // Source rows stream through a ring of four slots of G rows (one mbarrier each, three slots in flight while
+            // one is read); every row is staged once and its horizontal pass lives in registers, so output rows simply
+            // consume rows in order -- no per-output-row batches, which at scale 4 held a single row each.
             const int nt = warp_max_i32(xn);                      // uniform: taps evaluated per source row
             float w[6], c[6];
 #pragma unroll
@@ -597,73 +593,99 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                 c[k] = __fmul_rn(w[k], -8388608.0f);
                 asm volatile("" : "+f"(c[k]));
             }
+            const int s_first = __float_as_int(ydr[0].w) & 0xffffff;
+            const int ysn_last = __float_as_int(ydr[new_h - 1].w);
+            const int s_end = (ysn_last & 0xffffff) + (ysn_last >> 24);          // one past the last source row
+            const int G = min(32, (2 * WARP_BUF / pitch) >> 2);                  // rows per slot (lane r issues row r)
+            const int ngroups = (s_end - s_first + G - 1) / G;
+            const unsigned slot_bytes = (unsigned)(G * pitch);
+            unsigned bulkmask = 0;
+            auto issue = [&](int g) {
+                const int j = g & 3, lo = s_first + g * G;
+                const int bulk = warp_stage(wbase + j * slot_bytes, wbase_s + j * slot_bytes, bar_s + 8 * j, src_seg, rowstride, img_end,
+                                            lo, min(G, s_end - lo), pitch, lane, lr, lv, rpp);
+                bulkmask = (bulkmask & ~(1u << j)) | ((unsigned)bulk << j);
+            };
+            auto wait = [&](int g) {
+                const int j = g & 3;
+                if ((bulkmask >> j) & 1u) { mbar_wait(bar_s + 8 * j, (ph >> j) & 1u); ph ^= 1u << j; }
+                else cp_async_wait_all();
+                __syncwarp();
+            };
+            __syncwarp();                                   // previous item finished with the buffers
+            for (int g = 0; g < min(4, ngroups); ++g) issue(g);
+            wait(0);
+            int gi = 0, gend = s_first + G;                 // current group and one past its last row
             int crow = -1;
             u64 hc01 = 0ull;
             float hc2 = 0.f;
-            // the whole strip loop is instantiated per tap count so that the horizontal pass is straight-line code
             auto strip = [&](auto nt_c) {
                 constexpr int NT = decltype(nt_c)::value;
-                for (int b = 0; b < nb; ++b) {
-                    const int k = b & 1;
-                    if (bulk_cur) {
-                        if (k == 0) { mbar_wait(bar_s, phase0); phase0 ^= 1u; } else { mbar_wait(bar_s + 8, phase1); phase1 ^= 1u; }
-                    } else {
-                        cp_async_wait_all();
+                unsigned gbase = wbase_s + colc4 - (unsigned)(s_first * pitch);          // ALIGNED: row r of the group at gbase + r * pitch
+                auto hrow = [&](int row) {
+                    if (row >= gend) {
+                        do {
+                            __syncwarp();                   // every lane is done with slot gi & 3
+                            if (gi + 4 < ngroups) issue(gi + 4);
+                            ++gi;
+                            wait(gi);
+                            gend += G;
+                        } while (row >= gend);
+                        gbase = wbase_s + (unsigned)(gi & 3) * slot_bytes + colc4 - (unsigned)((gend - G) * pitch);
                     }
-                    __syncwarp();
-                    if (b + 1 < nb) s_lo_next = stage(b + 1, k ^ 1, ydn);
-                    ydn = load_desc(b + 2);
-                    const unsigned cur = wbase_s + k * WARP_BUF, ring = wbase_s + 2 * WARP_BUF + k * WARP_DESC;
-                    const int y0 = b * bh, cnt = min(bh, new_h - y0);
+                    if (ALIGNED) {
+                        h_area_n<NT>(gbase + (unsigned)(row * pitch), shc, w, c, hc01, hc2);
+                    } else {
+                        const int a = (row - (gend - G)) * pitch + colc + ((mis0 + row * misstep) & 15);
+                        h_area_n<NT>(wbase_s + (unsigned)(gi & 3) * slot_bytes + (a & ~3), (a & 3) * 8, w, c, hc01, hc2);
+                    }
+                };
+                float4 d = ydr[0];
+                for (int y = 0; y < new_h; ++y) {
+                    const float4 dn = ydr[min(y + 1, new_h - 1)];
+                    const int ysn = __float_as_int(d.w);
+                    const int ys = ysn & 0xffffff, n = ysn >> 24;
+                    if (ys != crow) hrow(ys);                // else: the previous output row ended on this source row
+                    u64 acc01 = fprod2(pack2(d.x, d.x), hc01, nz2);
+                    float acc2 = __fmul_rn(d.x, hc2);
+                    for (int t = 1; t < n; ++t) {
+                        hrow(ys + t);
+                        const float beta = (t == n - 1) ? d.z : d.y;
+                        acc01 = fadd2(acc01, fprod2(pack2(beta, beta), hc01, nz2));
+                        acc2 = __fadd_rn(acc2, __fmul_rn(beta, hc2));
+                    }
+                    crow = ys + n - 1;
                     if (active) {
-                        const unsigned abase = cur + colc4 - (unsigned)(s_lo_cur * pitch);     // ALIGNED: row r starts at abase + r * pitch
-                        auto hrow = [&](int row, unsigned a4) {
-                            if (ALIGNED) {
-                                h_area_n<NT>(a4, shc, w, c, hc01, hc2);
-                            } else {
-                                const int a = (row - s_lo_cur) * pitch + colc + ((mis0 + row * misstep) & 15);
-                                h_area_n<NT>(cur + (a & ~3), (a & 3) * 8, w, c, hc01, hc2);
-                            }
-                        };
-                        for (int r = 0; r < cnt; ++r) {
-                            const float4 d = lds_f4(ring + r * 16);
-                            const int ysn = __float_as_int(d.w);
-                            const int ys = ysn & 0xffffff, n = ysn >> 24;
-                            unsigned a4 = abase + (unsigned)(ys * pitch);
-                            if (ys != crow) hrow(ys, a4);            // else: the previous output row ended on this source row
-                            u64 acc01 = fprod2(pack2(d.x, d.x), hc01, nz2);
-                            float acc2 = __fmul_rn(d.x, hc2);
-                            for (int t = 1; t < n; ++t) {
-                                a4 += pitch;
-                                hrow(ys + t, a4);
-                                const float beta = (t == n - 1) ? d.z : d.y;
-                                acc01 = fadd2(acc01, fprod2(pack2(beta, beta), hc01, nz2));
-                                acc2 = __fadd_rn(acc2, __fmul_rn(beta, hc2));
-                            }
-                            crow = ys + n - 1;
-                            float a0f, a1f;
-                            unpack2(acc01, a0f, a1f);
-                            if (OUT_U8) {
-                                out.px(roi, dy0 + y0 + r, x, round_u8(a0f), round_u8(a1f), round_u8(acc2));
-                            } else {
-                                const unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
-                                optr[0] = lds_f32(swap ? l2 : l0);
-                                optr[plane] = lds_f32(l1 + 1024);
-                                optr[2 * plane] = lds_f32((swap ? l0 : l2) + 2048);
-                                optr += T;
-                            }
+                        float a0f, a1f;
+                        unpack2(acc01, a0f, a1f);
+                        if (OUT_U8) {
+                            out.px(roi, dy0 + y, x, round_u8(a0f), round_u8(a1f), round_u8(acc2));
+                        } else {
+                            const unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
+                            optr[0] = lds_f32(swap ? l2 : l0);
+                            optr[plane] = lds_f32(l1 + 1024);
+                            optr[2 * plane] = lds_f32((swap ? l0 : l2) + 2048);
+                            optr += T;
                         }
                     } else if (padlane) {
-                        for (int r = 0; r < cnt; ++r) out.pad(roi, dy0 + y0 + r, x);
+                        out.pad(roi, dy0 + y, x);
                     }
-                    s_lo_cur = s_lo_next;
-                    bulk_cur = bulk_next;
+                    d = dn;
                 }
             };
             if (nt <= 4) strip(std::integral_constant<int, 4>{});
             else if (nt == 5) strip(std::integral_constant<int, 5>{});
             else strip(std::integral_constant<int, 6>{});
-        } else if (cls == 1) {
+            continue;
+        }
+
+        __syncwarp();                                   // previous item finished with the buffers
+        int s_lo_cur = stage(0, 0, load_desc(0));
+        bulk_cur = bulk_next;
+        float4 ydn = load_desc(1);
+        int s_lo_next = 0;
+
+        if (cls == 1) {
             ColW cw;
             cw.set(xd.x, xd.y, xd.z);
             int crow = -1;
@@ -672,7 +694,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             for (int b = 0; b < nb; ++b) {
                 const int k = b & 1;
                 if (bulk_cur) {
-                    if (k == 0) { mbar_wait(bar_s, phase0); phase0 ^= 1u; } else { mbar_wait(bar_s + 8, phase1); phase1 ^= 1u; }
+                    mbar_wait(bar_s + 8 * k, (ph >> k) & 1u); ph ^= 1u << k;
                 } else {
                     cp_async_wait_all();
                 }
@@ -735,7 +757,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             for (int b = 0; b < nb; ++b) {
                 const int k = b & 1;
                 if (bulk_cur) {
-                    if (k == 0) { mbar_wait(bar_s, phase0); phase0 ^= 1u; } else { mbar_wait(bar_s + 8, phase1); phase1 ^= 1u; }
+                    mbar_wait(bar_s + 8 * k, (ph >> k) & 1u); ph ^= 1u << k;
                 } else {
                     cp_async_wait_all();
                 }
