@@ -24,6 +24,9 @@
 //                     streamed through shared memory in chunks (handles boxes as large as the image).
 // The dominant traffic is the float32 output (3*T*T*4 B per ROI): each warp stores 128 contiguous bytes per
 // plane and row; padding rows are written with 16-byte stores.
+#include <cuda.h>
+
+#include <mutex>
 #include <type_traits>
 
 #include "common.cuh"
@@ -34,7 +37,8 @@ constexpr int CROP_BAND = 8;                 // generic kernel: output rows per 
 constexpr int CROP_RAW_BYTES = 40 * 1024;    // generic kernel: staged source bytes
 constexpr int WARP_BUF = 3584;               // warp kernel: bytes of one staging buffer (two per warp)
 constexpr int WARP_DESC = 32 * 16;           // warp kernel: 32 row descriptors (two rings per warp)
-constexpr int WARP_SMEM = 2 * WARP_BUF + 2 * WARP_DESC + 32;   // + four mbarriers (classes 1 / 3 use two)
+constexpr int WARP_SMEM = 8320;              // 2 staging buffers + 2 descriptor rings + four mbarriers, padded to a multiple of 128
+static_assert(WARP_SMEM % 128 == 0 && WARP_SMEM >= 2 * WARP_BUF + 2 * WARP_DESC + 32 && WARP_BUF % 128 == 0, "TMA box destinations are 128-byte aligned");
 constexpr int WARPK_WARPS = 8;
 constexpr int WARPK_SMEM = WARPK_WARPS * WARP_SMEM + 768 * 4;
 constexpr int DESC_STRIDE = 256;             // descriptors per ROI and axis (T <= 256)
@@ -49,6 +53,17 @@ struct RoiGeom {                             // 88 bytes, workspace
     int pitch, pad_;
 };
 static_assert(sizeof(RoiGeom) == 88, "RoiGeom layout");
+
+// 2-D tensor maps over the image pool seen as [B*H rows][W*3/4 uint32] (only when W*3 is a multiple of 16): one map
+// per staging pitch, box = {pitch / 4 words, 4 rows} (2 rows for the two widest), so one TMA instruction stages four
+// source rows of a strip instead of one bulk copy per row; rows / columns beyond the pool are zero-filled by the TMA
+// unit, which removes the guarded tail path.
+constexpr int N_TMAPS = 15;
+struct TmapSet { CUtensorMap m[N_TMAPS]; };
+__host__ __device__ __forceinline__ int tmap_pitch(int need) { return need <= 448 ? (need < 64 ? 64 : ((need + 31) & ~31)) : ((need + 63) & ~63); }
+__host__ __device__ __forceinline__ int tmap_index(int pitch) { return pitch <= 448 ? (pitch - 64) / 32 : 13 + (pitch - 512) / 64; }
+__host__ __device__ __forceinline__ int tmap_rows(int pitch) { return pitch <= 448 ? 4 : 2; }
+constexpr int TMAP_MAX_PITCH = 576;
 
 struct YDesc {                               // generic kernel, per output row of the band
     int start;
@@ -184,7 +199,7 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                         const int seg_px = (int)(31.0 * g.scale_x) + (int)ceil(g.scale_x) + 3;
                         const int pitch_max = ((3 * seg_px + 46) >> 4) << 4;
                         const bool taps6 = (int)ceil(g.scale_x) + 1 <= 6 && (int)ceil(g.scale_y) + 1 <= 6;
-                        g.cls = (taps6 && 8 * pitch_max <= 2 * WARP_BUF) ? 4 : 2;      // ring slots of >= 2 rows
+                        g.cls = (taps6 && pitch_max <= TMAP_MAX_PITCH) ? 4 : 2;        // four ring slots of >= 2 rows fit 2 * WARP_BUF
                     } else g.cls = 2;
                 }
             }
@@ -464,6 +479,17 @@ __device__ __forceinline__ int warp_stage(unsigned char* buf, unsigned buf_s, un
     return 0;
 }
 
+// The same through a 2-D tensor map: box i = rows [row + i*rb, +rb) x pitch bytes from word column xw, issued by lane i.
+__device__ __forceinline__ void warp_stage_2d(unsigned buf_s, unsigned bar_s, const CUtensorMap* map, int xw, int row, int count,
+                                              int pitch, int rb, int lane) {
+    const int nboxes = (count + rb - 1) / rb;
+    if (lane == 0) mbar_expect_tx(bar_s, (unsigned)(nboxes * rb * pitch));
+    __syncwarp();
+    if (lane < nboxes)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     :: "r"(buf_s + (unsigned)(lane * rb * pitch)), "l"(map), "r"(xw), "r"(row + lane * rb), "r"(bar_s) : "memory");
+}
+
 __device__ __forceinline__ int warp_max_i32(int v) {
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, m));
@@ -477,8 +503,8 @@ __global__ void __launch_bounds__(256, 3)
 bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom,
                      const float4* __restrict__ xdesc, const float4* __restrict__ ydesc, int32_t* __restrict__ wcount,
                      int R, int Trt, int nslot, uchar4 fill, int swap_rb, const float* __restrict__ lut_g,
-                     float* __restrict__ outf, uint8_t* __restrict__ outb) {
-    extern __shared__ __align__(16) unsigned char smem[];
+                     float* __restrict__ outf, uint8_t* __restrict__ outb, const __grid_constant__ TmapSet tm) {
+    extern __shared__ __align__(128) unsigned char smem[];
     float* lut = reinterpret_cast<float*>(smem);                                 // [768]
     const int T = TT ? TT : Trt;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -542,16 +568,24 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
         const int xs_min = -warp_max_i32(-xs);
         const int xe_max = warp_max_i32(xs + xn);
         const int seg_bytes = 3 * (xe_max - xs_min);
-        const int pitch = ((15 + seg_bytes + 8 + 15) >> 4) << 4;
+        const int pitch_need = ((15 + seg_bytes + 8 + 15) >> 4) << 4;
+        const int pitch = ALIGNED ? tmap_pitch(pitch_need) : pitch_need;
+        const int rb = tmap_rows(pitch);                                  // rows per TMA box (ALIGNED)
+        const CUtensorMap* map = &tm.m[ALIGNED ? tmap_index(pitch) : 0];
         const int nv = pitch >> 4;
         const int rpp = 32 / nv, lr = lane / nv, lv = lane - lr * nv;
         const unsigned long long src_seg = gp->src + 3ull * (unsigned long long)xs_min;
         const int mis0 = (int)(src_seg & 15ull), misstep = ALIGNED ? 0 : (int)(rowstride & 15ull);
         const int colc = 3 * (xs - xs_min) + (ALIGNED ? mis0 : 0);
         const int colc4 = colc & ~3, shc = (colc & 3) * 8;
-        const int rows_fit = WARP_BUF / pitch;
+        const int rows_fit = ALIGNED ? (WARP_BUF / pitch) / rb * rb : WARP_BUF / pitch;
+        // tensor coordinates of the strip's first staged byte: flattened image row and uint32 column
+        const unsigned long long seg_off = (src_seg & ~15ull) - (unsigned long long)(uintptr_t)images;
+        const int row0 = ALIGNED ? (int)(seg_off / rowstride) : 0;
+        const int xw = ALIGNED ? (int)((seg_off - (unsigned long long)row0 * rowstride) >> 2) : 0;
         const double scale_y = gp->scale_y;
-        const int bh = max(1, min(32, (int)((double)(rows_fit - 3) / (scale_y < 1.0 ? 1.0 : scale_y))));
+        // bh output rows tap at most bh*scale + 2 source rows; whole TMA boxes round that up by rb - 1 more
+        const int bh = max(1, min(32, (int)((double)(rows_fit - (ALIGNED ? 5 : 3)) / (scale_y < 1.0 ? 1.0 : scale_y))));
         const int nb = (new_h + bh - 1) / bh;
         const float4* ydr = ydesc + (size_t)roi * DESC_STRIDE;
         float* optr = outf + ((size_t)roi * 3 * T + dy0) * T + x;     // (plane 0, current row, column x)
@@ -571,8 +605,13 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             }
             const int s_lo = __shfl_sync(0xffffffffu, lo, 0);
             const int s_hi = __shfl_sync(0xffffffffu, hi, cnt - 1);
-            bulk_next = warp_stage(wbase + k * WARP_BUF, wbase_s + k * WARP_BUF, bar_s + 8 * k, src_seg, rowstride, img_end, s_lo,
-                                   s_hi - s_lo + 1, pitch, lane, lr, lv, rpp);
+            if (ALIGNED) {
+                warp_stage_2d(wbase_s + k * WARP_BUF, bar_s + 8 * k, map, xw, row0 + s_lo, s_hi - s_lo + 1, pitch, rb, lane);
+                bulk_next = 1;
+            } else {
+                bulk_next = warp_stage(wbase + k * WARP_BUF, wbase_s + k * WARP_BUF, bar_s + 8 * k, src_seg, rowstride, img_end, s_lo,
+                                       s_hi - s_lo + 1, pitch, lane, lr, lv, rpp);
+            }
             return s_lo;
         };
         auto load_desc = [&](int b) -> float4 {
@@ -596,14 +635,17 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             const int s_first = __float_as_int(ydr[0].w) & 0xffffff;
             const int ysn_last = __float_as_int(ydr[new_h - 1].w);
             const int s_end = (ysn_last & 0xffffff) + (ysn_last >> 24);          // one past the last source row
-            const int G = min(32, (2 * WARP_BUF / pitch) >> 2);                  // rows per slot (lane r issues row r)
+            const int G = ALIGNED ? ((2 * WARP_BUF / pitch) >> 2) / rb * rb       // rows per slot: whole TMA boxes
+                                  : min(32, (2 * WARP_BUF / pitch) >> 2);       // (1-D copies: lane r issues row r)
             const int ngroups = (s_end - s_first + G - 1) / G;
             const unsigned slot_bytes = (unsigned)(G * pitch);
             unsigned bulkmask = 0;
             auto issue = [&](int g) {
                 const int j = g & 3, lo = s_first + g * G;
-                const int bulk = warp_stage(wbase + j * slot_bytes, wbase_s + j * slot_bytes, bar_s + 8 * j, src_seg, rowstride, img_end,
-                                            lo, min(G, s_end - lo), pitch, lane, lr, lv, rpp);
+                int bulk = 1;
+                if (ALIGNED) warp_stage_2d(wbase_s + j * slot_bytes, bar_s + 8 * j, map, xw, row0 + lo, min(G, s_end - lo), pitch, rb, lane);
+                else bulk = warp_stage(wbase + j * slot_bytes, wbase_s + j * slot_bytes, bar_s + 8 * j, src_seg, rowstride, img_end,
+                                       lo, min(G, s_end - lo), pitch, lane, lr, lv, rpp);
                 bulkmask = (bulkmask & ~(1u << j)) | ((unsigned)bulk << j);
             };
             auto wait = [&](int g) {
@@ -1023,6 +1065,46 @@ __global__ void bpc_lut_kernel(float m0, float m1, float m2, float s0, float s1,
     lut[t] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.f), mean), sd);
 }
 
+// Tensor maps of the image pool for every staging pitch (host side, cached for the last pool seen).  The driver entry
+// point is fetched through the runtime, so the library still links against cudart only.
+static int tensor_maps(const uint8_t* images, int B, int H, int W, bool aligned, const TmapSet** out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static std::mutex mu;
+    static TmapSet cached, empty;
+    static const uint8_t* k_images = nullptr;
+    static int k_B = 0, k_H = 0, k_W = 0, k_dev = -1;
+    static EncodeFn encode = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!aligned) { *out = &empty; return BPC_OK; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (images == k_images && B == k_B && H == k_H && W == k_W && dev == k_dev) { *out = &cached; return BPC_OK; }
+    if (!encode) {
+        cudaDriverEntryPointQueryResult q;
+        void* fnp = nullptr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return (int)e;
+        if (q != cudaDriverEntryPointSuccess || !fnp) return (int)cudaErrorNotSupported;
+        encode = (EncodeFn)fnp;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)W * 3 / 4, (cuuint64_t)B * H};
+    const cuuint64_t gstride[1] = {(cuuint64_t)W * 3};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int i = 0; i < N_TMAPS; ++i) {
+        const int pitch = i < 13 ? 64 + 32 * i : 512 + 64 * (i - 13);
+        const cuuint32_t box[2] = {(cuuint32_t)pitch / 4, (cuuint32_t)tmap_rows(pitch)};
+        const CUresult r = encode(&cached.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)images, gdim, gstride, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { k_images = nullptr; return (int)cudaErrorInvalidValue; }
+    }
+    k_images = images; k_B = B; k_H = H; k_W = W; k_dev = dev;
+    *out = &cached;
+    return BPC_OK;
+}
+
 // workspace: geom[R] | xdesc[R][256] | ydesc[R][256] | counters[16] | glist[R]
 static size_t ws_off_xdesc(int R) { return (((size_t)R * sizeof(RoiGeom)) + 15) & ~(size_t)15; }
 static size_t ws_off_ydesc(int R) { return ws_off_xdesc(R) + (size_t)R * DESC_STRIDE * sizeof(float4); }
@@ -1055,8 +1137,11 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
     const uchar4 f4 = make_uchar4(fill[0], fill[1], fill[2], 0);
     {
         typedef void (*WarpFn)(const uint8_t*, int, int, int, const RoiGeom*, const float4*, const float4*, int32_t*, int, int, int,
-                               uchar4, int, const float*, float*, uint8_t*);
+                               uchar4, int, const float*, float*, uint8_t*, const TmapSet);
         const bool aligned = ((long long)W * 3) % 16 == 0;
+        const TmapSet* tmaps = nullptr;
+        const int terr = tensor_maps(images, B, H, W, aligned, &tmaps);
+        if (terr != BPC_OK) return terr;
         WarpFn fn;
         const bool sw = swap_rb != 0;
 #define BPC_PICK(TTV)                                                                                                  \
@@ -1077,7 +1162,7 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, WARPK_SMEM) != cudaSuccess || per_sm < 1) per_sm = 1;
         const long long slots = (long long)sms * per_sm;
         const int grid = (int)(want < slots ? want : slots);
-        fn<<<grid, 256, WARPK_SMEM, st>>>(images, B, H, W, geom, xdesc, ydesc, wcount, R, T, nslot, f4, swap_rb, lut, outf, outb);
+        fn<<<grid, 256, WARPK_SMEM, st>>>(images, B, H, W, geom, xdesc, ydesc, wcount, R, T, nslot, f4, swap_rb, lut, outf, outb, *tmaps);
         BPC_LAUNCH_CHECK();
     }
     static bool attr_set[2] = {false, false};
