@@ -258,6 +258,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG') and not os.environ.get('NCCL_DEBUG_FILE'):
+            os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'       # keep NCCL's banner / log lines off stdout (one JSON line there)
         dist.init_process_group('nccl', device_id=dev)
     _lib.load()
 
