@@ -80,6 +80,36 @@ def test_random_boxes_all_regimes_full_res():
     assert seen == {1, 2, 3}
 
 
+@pytest.mark.parametrize('T,width', [(224, 1920), (64, 1920), (256, 1918), (100, 1913)])
+def test_large_boxes_four_to_six_taps(T, width):
+    """Boxes of 2T .. 5.3T: the 4 / 5 / 6-tap class of the warp kernel (row-streaming ring) and, beyond scale 5, the generic
+    kernel.  width 1920: image pitch a multiple of 16 bytes (2-D TMA staging); 1918 / 1913: the 1-D bulk-copy path."""
+    from bpc_baseline_b200 import batched, synth
+    imgs = synth.make_images(2, seed=9, width=width, height=1080)
+    rng = np.random.default_rng([23, T, width])
+    rois = []
+    for lo, hi in ((2.0, 3.0), (3.0, 4.0), (4.0, 5.0), (5.0, 5.3)):
+        for _ in range(10):
+            long_side = min(int(rng.uniform(lo, hi) * T), 1080)
+            short = int(rng.integers(max(8, long_side // 6), long_side + 1))
+            w, h = (long_side, short) if rng.random() < 0.5 else (short, long_side)
+            w = min(w, width)
+            x1 = int(rng.integers(0, width - w + 1)); y1 = int(rng.integers(0, 1080 - h + 1))
+            rois.append((int(rng.integers(0, 2)), x1, y1, x1 + w, y1 + h))
+    # exact integer-ish ratios next to the class boundaries, and the bottom-right corner of the last image
+    rois += [(1, width - 4 * T - 1 if width > 4 * T + 1 else 0, 0, width, min(1080, 4 * T + 1)),
+             (1, max(0, width - 5 * T), 1080 - min(1080, 3 * T), width, 1080), (0, 0, 0, min(width, 4 * T + 3), min(1080, 2 * T + 1))]
+    rois = np.asarray(rois, np.int32)
+    out = batched.roi_crop_u8(to_dev(imgs), to_dev(rois), T=T).cpu().numpy()
+    outf = batched.roi_crop(to_dev(imgs), to_dev(rois), T=T, swap_rb=True).cpu().numpy()
+    lut = batched.normalise_lut('cuda').cpu().numpy()
+    for r, (b, x1, y1, x2, y2) in enumerate(rois):
+        want = ocrop.crop_u8_ref(imgs[b], (x1, y1, x2, y2), T)
+        assert np.array_equal(out[r], want), (r, tuple(rois[r]))
+        wantf = np.stack([lut[p][want[..., 2 - p]] for p in range(3)])
+        assert np.array_equal(outf[r], wantf), (r, tuple(rois[r]))
+
+
 def test_rejected_rois_and_device_count():
     from bpc_baseline_b200 import batched, synth
     imgs = to_dev(synth.make_images(1, seed=6, width=640, height=480))
