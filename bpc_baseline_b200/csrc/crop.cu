@@ -733,6 +733,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             int crow = -1;
             u64 hc01 = 0ull;
             float hc2 = 0.f;
+            unsigned roff = 0;                                // element offset of the current output row from optr
             for (int b = 0; b < nb; ++b) {
                 const int k = b & 1;
                 if (bulk_cur) {
@@ -746,8 +747,10 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                 const unsigned cur = wbase_s + k * WARP_BUF, ring = wbase_s + 2 * WARP_BUF + k * WARP_DESC;
                 const int y0 = b * bh, cnt = min(bh, new_h - y0);
                 if (active) {
+                    float4 dnx = lds_f4(ring);
                     for (int r = 0; r < cnt; ++r) {
-                        const float4 d = lds_f4(ring + r * 16);
+                        const float4 d = dnx;
+                        dnx = lds_f4(ring + (r + 1) * 16);          // next row's descriptor in flight behind this row's arithmetic
                         const int ysn = __float_as_int(d.w);
                         const int ys = ysn & 0xffffff, n = ysn >> 24;
                         // byte address of the lane's first tap in row ys; with a 16-byte-multiple image pitch the
@@ -780,10 +783,11 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                         } else {
                             // bits(v + 2^23) = 0x4B000000 + cvRound(v): the LUT address is one multiply-add away
                             const unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
-                            optr[0] = lds_f32(swap ? l2 : l0);
-                            optr[plane] = lds_f32(l1 + 1024);
-                            optr[2 * plane] = lds_f32((swap ? l0 : l2) + 2048);
-                            optr += T;
+                            float* o = optr + roff;               // fresh address registers per row: no wait on the previous row's stores
+                            o[0] = lds_f32(swap ? l2 : l0);
+                            o[plane] = lds_f32(l1 + 1024);
+                            o[2 * plane] = lds_f32((swap ? l0 : l2) + 2048);
+                            roff += (unsigned)T;
                         }
                     }
                 } else if (padlane) {
