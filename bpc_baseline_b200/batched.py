@@ -260,9 +260,11 @@ MAX_ROIS_PER_LAUNCH = 32768
 
 
 def _crop_workspace(dev, R: int) -> torch.Tensor:
-    """Device scratch for the crop kernels, cached per device and grown on demand."""
+    """Device scratch for the crop kernels, cached per (device, stream) and grown on demand.
+
+    Keyed by the current stream as well: two streams cropping concurrently must not share tap descriptors."""
     need = int(_lib.load().bpc_roi_crop_workspace_bytes(int(R)))
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), int(torch.cuda.current_stream(dev).cuda_stream))
     ws = _WS_CACHE.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.empty((max(need, 1 << 16),), dtype=torch.uint8, device=dev)

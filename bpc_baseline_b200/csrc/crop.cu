@@ -26,6 +26,8 @@
 // plane and row; padding rows are written with 16-byte stores.
 #include <cuda.h>
 
+#include <string.h>
+
 #include <mutex>
 #include <type_traits>
 
@@ -1071,20 +1073,20 @@ __global__ void bpc_lut_kernel(float m0, float m1, float m2, float s0, float s1,
 
 // Tensor maps of the image pool for every staging pitch (host side, cached for the last pool seen).  The driver entry
 // point is fetched through the runtime, so the library still links against cudart only.
-static int tensor_maps(const uint8_t* images, int B, int H, int W, bool aligned, const TmapSet** out) {
+static int tensor_maps(const uint8_t* images, int B, int H, int W, bool aligned, TmapSet* out) {
     typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
     static std::mutex mu;
-    static TmapSet cached, empty;
+    static TmapSet cached;
     static const uint8_t* k_images = nullptr;
     static int k_B = 0, k_H = 0, k_W = 0, k_dev = -1;
     static EncodeFn encode = nullptr;
     std::lock_guard<std::mutex> lock(mu);
-    if (!aligned) { *out = &empty; return BPC_OK; }
+    if (!aligned) { memset(out, 0, sizeof(TmapSet)); return BPC_OK; }      // the 1-D bulk-copy variants ignore the maps
     int dev = 0;
     cudaGetDevice(&dev);
-    if (images == k_images && B == k_B && H == k_H && W == k_W && dev == k_dev) { *out = &cached; return BPC_OK; }
+    if (images == k_images && B == k_B && H == k_H && W == k_W && dev == k_dev) { *out = cached; return BPC_OK; }   // copied under the lock
     if (!encode) {
         cudaDriverEntryPointQueryResult q;
         void* fnp = nullptr;
@@ -1105,7 +1107,7 @@ static int tensor_maps(const uint8_t* images, int B, int H, int W, bool aligned,
         if (r != CUDA_SUCCESS) { k_images = nullptr; return (int)cudaErrorInvalidValue; }
     }
     k_images = images; k_B = B; k_H = H; k_W = W; k_dev = dev;
-    *out = &cached;
+    *out = cached;
     return BPC_OK;
 }
 
@@ -1143,7 +1145,7 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
         typedef void (*WarpFn)(const uint8_t*, int, int, int, const RoiGeom*, const float4*, const float4*, int32_t*, int, int, int,
                                uchar4, int, const float*, float*, uint8_t*, const TmapSet);
         const bool aligned = ((long long)W * 3) % 16 == 0;
-        const TmapSet* tmaps = nullptr;
+        TmapSet tmaps;
         const int terr = tensor_maps(images, B, H, W, aligned, &tmaps);
         if (terr != BPC_OK) return terr;
         WarpFn fn;
@@ -1166,7 +1168,7 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, WARPK_SMEM) != cudaSuccess || per_sm < 1) per_sm = 1;
         const long long slots = (long long)sms * per_sm;
         const int grid = (int)(want < slots ? want : slots);
-        fn<<<grid, 256, WARPK_SMEM, st>>>(images, B, H, W, geom, xdesc, ydesc, wcount, R, T, nslot, f4, swap_rb, lut, outf, outb, *tmaps);
+        fn<<<grid, 256, WARPK_SMEM, st>>>(images, B, H, W, geom, xdesc, ydesc, wcount, R, T, nslot, f4, swap_rb, lut, outf, outb, tmaps);
         BPC_LAUNCH_CHECK();
     }
     static bool attr_set[2] = {false, false};

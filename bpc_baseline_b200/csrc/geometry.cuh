@@ -114,6 +114,7 @@ struct Scene {
     double* lines;     // [6][Dmax][3]   0:l2_12[i] 1:l1_12[j] 2:l2_13[i] 3:l1_13[k] 4:l2_23[j] 5:l1_23[k]
     uint8_t* lvalid;   // [6][Dmax]
     int N, M, P, Dmax;
+    unsigned long long m_magic;   // 2^40 / M + 1: r / M == (r * m_magic) >> 40 for r * M < 2^40
 
     __device__ __forceinline__ const double* pt(int cam, int d) const { return pts + ((size_t)cam * Dmax + d) * 2; }
     __device__ __forceinline__ const double* line(int set, int d) const { return lines + ((size_t)set * Dmax + d) * 3; }
@@ -123,8 +124,10 @@ struct Scene {
     __device__ __forceinline__ double pair(int set_l2, int set_l1, int cam_a, int a, int cam_b, int b) const {
         const double* pa = pt(cam_a, a);
         const double* pb = pt(cam_b, b);
-        const double d1 = valid(set_l1, b) ? line_point(line(set_l1, b), pa[0], pa[1]) : 9999.0;
-        const double d2 = valid(set_l2, a) ? line_point(line(set_l2, a), pb[0], pb[1]) : 9999.0;
+        // a degenerate line is stored as (0, 0, 9999): |fma(9999, 1, fma(0, y, 0 * x))| = 9999 exactly for finite x, y,
+        // i.e. the sentinel of :25-26 without a validity load and select per evaluation
+        const double d1 = line_point(line(set_l1, b), pa[0], pa[1]);
+        const double d2 = line_point(line(set_l2, a), pb[0], pb[1]);
         return dmul(0.5, dadd(d1, d2));
     }
     __device__ __forceinline__ double e12(int i, int j) const { return pair(0, 1, 0, i, 1, j); }
@@ -159,7 +162,7 @@ __device__ inline void scene_load(Scene& sc, const double* F, const double* cent
         double l[3];
         const bool ok = epiline(F + set_F[set] * 9, set_T[set], p[0], p[1], l);
         double* dst = sc.lines + (size_t)e * 3;
-        dst[0] = l[0]; dst[1] = l[1]; dst[2] = l[2];
+        dst[0] = ok ? l[0] : 0.0; dst[1] = ok ? l[1] : 0.0; dst[2] = ok ? l[2] : 9999.0;
         sc.lvalid[e] = ok ? 1 : 0;
     }
 }

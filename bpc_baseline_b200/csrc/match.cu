@@ -25,7 +25,7 @@ struct VirtualCost {            // cost.reshape(N*M, P) of the epipolar cost ten
     __device__ __forceinline__ double cost(int row, int col) const {
         const int r = transposed ? col : row;
         const int k = transposed ? row : col;
-        const int i = r / sc->M, j = r - i * sc->M;
+        const int i = (int)(((unsigned long long)(unsigned)r * sc->m_magic) >> 40), j = r - i * sc->M;
         return (double)sc->cost(i, j, k);
     }
 };
@@ -207,6 +207,7 @@ __global__ void __launch_bounds__(256, 2) bpc_match_kernel(const float* __restri
         __syncthreads();                                   // previous scene fully written out
         Scene& sc = ms.sc;
         sc.N = counts[s * 3 + 0]; sc.M = counts[s * 3 + 1]; sc.P = counts[s * 3 + 2];
+        sc.m_magic = sc.M > 0 ? (1ull << 40) / (unsigned long long)sc.M + 1ull : 0ull;
         const float* K = Ks + (size_t)s * 27;
         const double* RT = RTs + (size_t)s * 48;
         // ---- phase 0 ---------------------------------------------------------------------------------
@@ -412,6 +413,7 @@ __global__ void bpc_cost_tensor_kernel(const double* __restrict__ F, const doubl
         __syncthreads();
         if (tid < 27) Fs[tid] = F[(size_t)s * 27 + tid];
         sc.N = counts[s * 3 + 0]; sc.M = counts[s * 3 + 1]; sc.P = counts[s * 3 + 2];
+        sc.m_magic = sc.M > 0 ? (1ull << 40) / (unsigned long long)sc.M + 1ull : 0ull;
         __syncthreads();
         if (sc.N < 0 || sc.M < 0 || sc.P < 0 || sc.N > Dmax || sc.M > Dmax || sc.P > Dmax) continue;
         scene_load(sc, Fs, centers + (size_t)s * 3 * Dmax * 2, nth, tid);
