@@ -90,8 +90,9 @@ __device__ void row_argmin(const Scene& sc, int k, double* sa, double* sb, short
     if (i0 >= N) i0 = 0;       // all-NaN guards
     if (j0 >= M) j0 = 0;
     __syncwarp();
-    // seed an upper bound from the row / column through the individually best i and j
-    double best = INF;
+    // seed an upper bound: first the sum at (i0, j0) itself (for a clean scene that already is the minimum and prunes
+    // nearly every candidate below), then the row / column through the individually best i and j
+    double best = dadd(dadd(sc.e12(i0, j0), sa[i0]), sb[j0]);
     for (int j = lane; j < M; j += 32)
         if (sb[j] <= best) best = fmin(best, dadd(dadd(sc.e12(i0, j), sa[i0]), sb[j]));
     for (int i = lane; i < N; i += 32)
