@@ -140,6 +140,31 @@ __device__ __forceinline__ int lsap_pos(const LsapState& st, int col, int remove
     return st.nc - 1 - col;                          // unreachable for a live column
 }
 
+// Label of one unassigned column over the chain 0..t (first minimum wins = SciPy's strict `<` update) as a candidate.
+template <class Acc>
+__device__ __forceinline__ Cand lsap_label(const LsapState& st, const Acc& acc, int col, int t, int nov) {
+    double spc = __longlong_as_double(0x7ff0000000000000LL);
+    int tau = -1;
+    for (int a = 0; a <= t; ++a) {
+        const double r = dsub(dadd(st.cm[a], acc.cost(st.crow[a], col)), st.cu[a]);
+        if (r < spc) { spc = r; tau = a; }
+    }
+    Cand c;
+    c.val = spc; c.col = col; c.tau = tau; c.row = -1;
+    c.key = (1 << 30) + lsap_pos(st, col, t, nov);
+    return c;
+}
+
+// Exhaustive scan of the unassigned columns (what SciPy does); every thread folds its columns into `best`.
+template <class Acc>
+__device__ inline void lsap_scan_unassigned_full(const LsapState& st, const Acc& acc, int t, int nov, Cand& best, int nthreads, int tid) {
+    for (int col = tid; col < st.nc; col += nthreads) {
+        if (st.assigned(col)) continue;
+        const Cand c = lsap_label(st, acc, col, t, nov);
+        if (cand_better(c, best)) best = c;
+    }
+}
+
 // One shortest-augmenting-path search + dual update + augmentation for row `cur`.
 // Collective over the CTA.  Acc::cost(row, col) returns the float32 cost widened to double.
 // Returns with st.ctl[2] != 0 if the problem is infeasible (all-infinite / NaN row).
@@ -155,20 +180,8 @@ __device__ void lsap_augment(LsapState& st, const Acc& acc, int cur, int nthread
         const int nov = st.ctl[3];
         Cand best;
         best.val = __longlong_as_double(0x7ff0000000000000LL); best.key = -1; best.col = -1; best.tau = -1; best.row = -1;
-        // unassigned columns: v == 0
-        for (int col = tid; col < nc; col += nthreads) {
-            if (st.assigned(col)) continue;
-            double spc = __longlong_as_double(0x7ff0000000000000LL);
-            int tau = -1;
-            for (int a = 0; a <= t; ++a) {
-                const double r = dsub(dadd(st.cm[a], acc.cost(st.crow[a], col)), st.cu[a]);
-                if (r < spc) { spc = r; tau = a; }
-            }
-            Cand c;
-            c.val = spc; c.col = col; c.tau = tau; c.row = -1;
-            c.key = (1 << 30) + lsap_pos(st, col, t, nov);
-            if (cand_better(c, best)) best = c;
-        }
+        // unassigned columns: v == 0 (the accessor may enumerate only columns that can attain the minimum)
+        acc.scan_unassigned(st, t, nov, best, nthreads, tid);
         // assigned columns not yet in the tree, one per owning row
         for (int i = tid; i < nr; i += nthreads) {
             const int col = st.col4row[i];

@@ -19,15 +19,21 @@ namespace bpc {
 // ------------------------------------------------------------------------------------------------------
 // cost accessors for the assignment
 // ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_min_d(double v);
+__device__ __forceinline__ int warp_min_i(int v);
+
 struct VirtualCost {            // cost.reshape(N*M, P) of the epipolar cost tensor
     const Scene* sc;
     int transposed;             // 1: rows = k, cols = r = i*M + j   (N*M > P, SciPy transposes)
+    // per-warp scratch for the pruned column scan (the phase-1 buffers, free during the assignment); null = scan everything
+    double* wa; double* wb; short* wil; short* wjl;
     __device__ __forceinline__ double cost(int row, int col) const {
         const int r = transposed ? col : row;
         const int k = transposed ? row : col;
         const int i = (int)(((unsigned long long)(unsigned)r * sc->m_magic) >> 40), j = r - i * sc->M;
         return (double)sc->cost(i, j, k);
     }
+    __device__ void scan_unassigned(const LsapState& st, int t, int nov, Cand& best, int nthreads, int tid) const;
 };
 
 struct ExplicitCost {           // dense float32 [N*M][P]
@@ -38,6 +44,9 @@ struct ExplicitCost {           // dense float32 [N*M][P]
         const int r = transposed ? col : row;
         const int k = transposed ? row : col;
         return (double)c[(size_t)r * P + k];
+    }
+    __device__ __forceinline__ void scan_unassigned(const LsapState& st, int t, int nov, Cand& best, int nthreads, int tid) const {
+        lsap_scan_unassigned_full(st, *this, t, nov, best, nthreads, tid);
     }
 };
 
@@ -137,6 +146,99 @@ __device__ void row_argmin(const Scene& sc, int k, double* sa, double* sb, short
     rlo = warp_min_i(rlo);
     if (lane == 0) { out.cmin[k] = cmin; out.cnt[k] = cnt; out.rlo[k] = rlo; }
     __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// phase 2 helper: the Dijkstra step's scan over the (up to 40 000) unassigned columns, pruned
+// ------------------------------------------------------------------------------------------------------
+// The step needs the unassigned column with the lowest label min_a r_a(col), r_a = (cm[a] + cost(k_a, col)) - cu[a],
+// ties resolved by SciPy's scan position.  r_a is monotone in the cost and cost(k, (i, j)) = f32(sum / 3) with
+// sum >= e13[i, k] and sum >= e23[j, k] (phase 1), so for each chain row a one warp (i) evaluates a_i = e13[i, k_a] and
+// b_j = e23[j, k_a], (ii) takes an upper bound on the minimum from the unassigned columns of row i0 = argmin a and
+// column j0 = argmin b, (iii) turns it into a bound on the sum, and (iv) labels only the columns (i, j) with a_i and b_j
+// below that bound -- every column that attains the true minimum is among them (in the enumeration of the chain row
+// that gives its label), each is labelled exactly over the whole chain, and the usual (value, position) order picks
+// the winner: the result is identical to the exhaustive scan.
+__device__ void VirtualCost::scan_unassigned(const LsapState& st, int t, int nov, Cand& best, int nthreads, int tid) const {
+    if (!transposed || wa == nullptr) {
+        lsap_scan_unassigned_full(st, *this, t, nov, best, nthreads, tid);
+        return;
+    }
+    const Scene& S = *sc;
+    const int lane = tid & 31, w = tid >> 5, nw = (nthreads + 31) >> 5;
+    const int N = S.N, M = S.M, D = S.Dmax;
+    double* sa = wa + (size_t)w * D;
+    double* sb = wb + (size_t)w * D;
+    short* il = wil + (size_t)w * D;
+    short* jl = wjl + (size_t)w * D;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    for (int a = w; a <= t; a += nw) {
+        const int k = st.crow[a];
+        const double cm = st.cm[a], cu = st.cu[a];
+        double amin = INF, bmin = INF;
+        int i0 = 0x7fffffff, j0 = 0x7fffffff;
+        for (int i = lane; i < N; i += 32) {
+            const double v = S.e13(i, k);
+            sa[i] = v;
+            if (v < amin) { amin = v; i0 = i; }
+        }
+        for (int j = lane; j < M; j += 32) {
+            const double v = S.e23(j, k);
+            sb[j] = v;
+            if (v < bmin) { bmin = v; j0 = j; }
+        }
+        const double wamin = warp_min_d(amin), wbmin = warp_min_d(bmin);
+        i0 = warp_min_i(amin == wamin ? i0 : 0x7fffffff);
+        j0 = warp_min_i(bmin == wbmin ? j0 : 0x7fffffff);
+        if (i0 >= N) i0 = 0;
+        if (j0 >= M) j0 = 0;
+        __syncwarp();
+        // upper bound on the lowest label: any unassigned column's r_a
+        double rub = INF;
+        for (int j = lane; j < M; j += 32)
+            if (!st.assigned(i0 * M + j))
+                rub = fmin(rub, dsub(dadd(cm, (double)cost_from_sum(dadd(dadd(S.e12(i0, j), sa[i0]), sb[j]))), cu));
+        for (int i = lane; i < N; i += 32)
+            if (!st.assigned(i * M + j0))
+                rub = fmin(rub, dsub(dadd(cm, (double)cost_from_sum(dadd(dadd(S.e12(i, j0), sa[i]), sb[j0]))), cu));
+        rub = warp_min_d(rub);
+        // r_a(c) <= rub  =>  c <= (rub + cu - cm) up to rounding of the two additions  =>  sum <= 3 c (1 + 2^-23)
+        double sbound = INF;
+        if (rub < INF) {
+            const double cb = dadd(dadd(dsub(rub, cm), cu), dmul(1e-9, dadd(dadd(fabs(rub), fabs(cm)), dadd(fabs(cu), 1.0))));
+            sbound = dadd(dmul(dmul(3.0, cb), 1.0 + 2.384185791015625e-07), 1e-30);
+        }
+        int nI = 0, nJ = 0;
+        for (int base = 0; base < N; base += 32) {
+            const int i = base + lane;
+            const bool p = i < N && sa[i] <= sbound;
+            const unsigned m = __ballot_sync(0xffffffffu, p);
+            if (p) il[nI + __popc(m & ((1u << lane) - 1))] = (short)i;
+            nI += __popc(m);
+        }
+        for (int base = 0; base < M; base += 32) {
+            const int j = base + lane;
+            const bool p = j < M && sb[j] <= sbound;
+            const unsigned m = __ballot_sync(0xffffffffu, p);
+            if (p) jl[nJ + __popc(m & ((1u << lane) - 1))] = (short)j;
+            nJ += __popc(m);
+        }
+        __syncwarp();
+        const int npair = nI * nJ;
+        double lub = rub;                                      // tightens as this lane finds candidates
+        for (int q = lane; q < npair; q += 32) {
+            const int ii = q / nJ, jj = q - ii * nJ;
+            const int i = il[ii], j = jl[jj];
+            const int col = i * M + j;
+            if (st.assigned(col)) continue;
+            const double ra = dsub(dadd(cm, (double)cost_from_sum(dadd(dadd(S.e12(i, j), sa[i]), sb[j]))), cu);
+            if (ra > lub) continue;                            // cannot be (or tie) the minimum
+            const Cand c = lsap_label(st, *this, col, t, nov);
+            if (cand_better(c, best)) best = c;
+            lub = fmin(lub, c.val);
+        }
+        __syncwarp();                                          // the scratch is reused by this warp's next chain row
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -249,6 +351,7 @@ __global__ void __launch_bounds__(256, 2) bpc_match_kernel(const float* __restri
         // ---- phase 2 ---------------------------------------------------------------------------------
         VirtualCost acc;
         acc.sc = &sc; acc.transposed = transposed;
+        acc.wa = ms.wa; acc.wb = ms.wb; acc.wil = ms.wil; acc.wjl = ms.wjl;
         LsapState& st = ms.st;
         int row = 0;
         for (;;) {

@@ -98,6 +98,18 @@ def test_config3_dense_bin_with_dropped_detections():
     _check_against_oracle(batch, out, [0, 300])
 
 
+@pytest.mark.parametrize('D,p_drop,sigma,n_dup,n_false,nscenes', [(48, 0.25, 3.0, 3, 3, 96), (96, 0.15, 2.0, 5, 4, 32),
+                                                                 (200, 0.1, 2.0, 0, 0, 6), (200, 0.3, 3.0, 6, 6, 4)])
+def test_conflict_heavy_scenes_match_scipy(D, p_drop, sigma, n_dup, n_false, nscenes):
+    """Every scene here runs the full shortest-augmenting-path search several times (dropped, duplicated and false
+    detections): the pruned column scan of the Dijkstra step must reproduce SciPy's choice of optimum, scene by scene."""
+    from bpc_baseline_b200 import synth
+    batch = synth.make_scenes(nscenes, D, p_drop=p_drop, sigma=sigma, n_dup=n_dup, n_false=n_false, seed=synth.SEED + 57)
+    out = _match(batch)
+    _check_properties(batch, out)
+    _check_against_oracle(batch, out, range(nscenes))
+
+
 def test_config5_131072_scenes_in_shards():
     """Config 5 on one GPU: the 131 072-scene stream in 8 shards of 16 384 (what 8 ranks would each take)."""
     from bpc_baseline_b200 import distributed, synth
