@@ -1144,7 +1144,8 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
     {
         typedef void (*WarpFn)(const uint8_t*, int, int, int, const RoiGeom*, const float4*, const float4*, int32_t*, int, int, int,
                                uchar4, int, const float*, float*, uint8_t*, const TmapSet);
-        const bool aligned = ((long long)W * 3) % 16 == 0;
+        // 2-D TMA staging needs a 16-byte image pitch; rows narrower than the widest box keep the 1-D path
+        const bool aligned = ((long long)W * 3) % 16 == 0 && (long long)W * 3 >= TMAP_MAX_PITCH;
         TmapSet tmaps;
         const int terr = tensor_maps(images, B, H, W, aligned, &tmaps);
         if (terr != BPC_OK) return terr;

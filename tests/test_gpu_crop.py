@@ -110,6 +110,33 @@ def test_large_boxes_four_to_six_taps(T, width):
         assert np.array_equal(outf[r], wantf), (r, tuple(rois[r]))
 
 
+@pytest.mark.parametrize('width', [16, 64, 176, 192, 208, 256])
+def test_small_images_with_16_byte_pitch(width):
+    """Image rows of 48 .. 768 bytes, all multiples of 16: below 576 bytes (the widest staging box) the 1-D copy path is
+    used, from 192 px on the 2-D tensor-map path whose boxes may then be as wide as, or wider than, what is left of a row."""
+    from bpc_baseline_b200 import batched, synth
+    H = 120
+    imgs = synth.make_images(3, seed=12, width=width, height=H)
+    rng = np.random.default_rng([31, width])
+    rois = [(2, 0, 0, width, H), (2, width - min(width, 9), H - 7, width, H), (0, 0, 0, min(width, 8), 8)]
+    for _ in range(40):
+        w = int(rng.integers(2, width + 1)); h = int(rng.integers(2, H + 1))
+        x1 = int(rng.integers(0, width - w + 1)); y1 = int(rng.integers(0, H - h + 1))
+        rois.append((int(rng.integers(0, 3)), x1, y1, x1 + w, y1 + h))
+    rois = np.asarray(rois, np.int32)
+    for T in (64, 224):
+        status = torch.zeros(len(rois), dtype=torch.int32, device='cuda')
+        out = batched.roi_crop_u8(to_dev(imgs), to_dev(rois), T=T, status=status).cpu().numpy()
+        st = status.cpu().numpy()
+        for r, (b, x1, y1, x2, y2) in enumerate(rois):
+            _, nw, nh, _, _ = ocrop.letterbox_geometry(y2 - y1, x2 - x1, T)
+            if nw < 1 or nh < 1:
+                assert st[r] == 1
+                continue
+            assert st[r] == 0
+            assert np.array_equal(out[r], ocrop.crop_u8_ref(imgs[b], (x1, y1, x2, y2), T)), (T, r, tuple(rois[r]))
+
+
 def test_rejected_rois_and_device_count():
     from bpc_baseline_b200 import batched, synth
     imgs = to_dev(synth.make_images(1, seed=6, width=640, height=480))
