@@ -258,8 +258,9 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        if os.environ.get('NCCL_DEBUG') and not os.environ.get('NCCL_DEBUG_FILE'):
-            os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'       # keep NCCL's banner / log lines off stdout (one JSON line there)
+        # NCCL writes its version banner / log lines to stdout (the level may come from /etc/nccl.conf, not the
+        # environment); stdout carries the one JSON line, so send them to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=dev)
     _lib.load()
 
