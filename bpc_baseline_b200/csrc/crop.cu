@@ -193,7 +193,9 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                         g.regime = 3;
                     }
                     g.src = (unsigned long long)(uintptr_t)images + (((unsigned long long)img * H + y1) * W + x1) * 3ull;
-                    if (g.regime == 1 && g.scale_x < 2.0 && g.scale_y < 2.0) g.cls = 1;
+                    // scale exactly 1 (long side == T) is OpenCV's integer-ratio regime, but a 1 x 1 box sum is the byte itself and
+                    // so is the area pass with its single tap of weight 1.0f: keep it on the fast path
+                    if ((g.regime == 1 && g.scale_x < 2.0 && g.scale_y < 2.0) || (g.regime == 2 && g.isx == 1 && g.isy == 1)) g.cls = 1;
                     else if (g.regime == 3) g.cls = 3;
                     else if (g.regime == 1) {
                         // general tap counts in the warp kernel if a strip's rows fit its staging buffer:
