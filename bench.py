@@ -417,10 +417,10 @@ def main():
         avg_launch_s = crop_ms * 1e-3 / crop_launches
         achieved = per_launch_bytes / avg_launch_s / 1e9
         # DRAM bytes of one full 16384-ROI launch of the default workload from the committed ncu --set full capture
-        # (profiles/r01_crop_warp_kernel_ncu.txt: dram__bytes_read.sum 3.063 GB + dram__bytes_write.sum 9.807 GB)
+        # (profiles/r01_crop_warp_kernel_ncu.txt: dram__bytes_read.sum 3.069 GB + dram__bytes_write.sum 9.835 GB)
         default_wl = (S, D, T, args.chunk_rois, args.pool, args.p_drop, args.sigma) == (4096, 20, 224, 16384, 8, 0.0, 1.0)
         roofline = {'bound': 'hbm', 'kernel': 'bpc_crop_warp_kernel<false,224,true,true> (+ prep, generic)', 'achieved': achieved,
-                    'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': 12.870e9 if default_wl else None,
+                    'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': 12.905e9 if default_wl else None,
                     'traffic_source': 'ncu capture of a full 16384-ROI launch, bytes' if default_wl else None,
                     'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': per_launch_bytes, 'avg_launch_ms': avg_launch_s * 1e3,
