@@ -198,20 +198,7 @@ class PoseEstimator:
                                'crop_inputs() returns the network inputs on their own')
         with torch.no_grad():
             raw = self.pose_model(tens).float().cpu()
-        mode = self.rotation_mode
-        if mode is None:
-            mode = {3: 'euler', 4: 'quat', 6: '6d'}.get(raw.shape[1])
-        if mode == 'euler':
-            wrapped = ((raw.numpy() + np.pi) % (2 * np.pi)) - np.pi
-            rot = rotmat_from_euler(torch.tensor(wrapped, dtype=torch.float32))
-        elif mode == 'quat':
-            q = raw / (raw.norm(dim=1, keepdim=True) + 1e-8)
-            rot = quat_to_rotmat(q)
-        elif mode == '6d':
-            rot = rotmat_from_6d(raw)
-        else:
-            raise ValueError("Unsupported rotation mode.")
-        rot = rot.numpy()
+        rot = decode_rotations(raw, self.rotation_mode)
         r = 0
         for p in predictions:
             p.rotation_preds = []
@@ -220,6 +207,24 @@ class PoseEstimator:
                 r += 1
             p.final_rotation = p.rotation_preds[2]
             p.pose = calc_pose_matrix(p.final_rotation, p.t)
+
+
+def decode_rotations(raw: torch.Tensor, mode=None) -> np.ndarray:
+    """Raw network outputs [n, 3 | 4 | 6] (CPU float32) -> rotation matrices [n, 3, 3] float32, batched form of the
+    per-crop decode in reference process_pose.py:213-229: euler angles are wrapped to [-pi, pi) in NumPy first (:215),
+    quaternions are normalised with eps 1e-8 (:220-222).  ``mode`` None picks the head from the output width."""
+    if mode is None:
+        mode = {3: 'euler', 4: 'quat', 6: '6d'}.get(raw.shape[1])
+    if mode == 'euler':
+        wrapped = ((raw.numpy() + np.pi) % (2 * np.pi)) - np.pi
+        rot = rotmat_from_euler(torch.tensor(wrapped, dtype=torch.float32))
+    elif mode == 'quat':
+        rot = quat_to_rotmat(raw / (raw.norm(dim=1, keepdim=True) + 1e-8))
+    elif mode == '6d':
+        rot = rotmat_from_6d(raw)
+    else:
+        raise ValueError("Unsupported rotation mode.")
+    return rot.numpy()
 
 
 # ---- rotation decoders of the pose head (reference bpc/pose/models/losses.py:26-84; off the hot path) ----

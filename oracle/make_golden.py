@@ -275,6 +275,55 @@ def golden_dataset(ref):
     print(f'  dataset: {len(boxes)} samples at T={T} (order after the constructor shuffle)')
 
 
+def golden_rotation(ref):
+    """rotation.npz: the decode + pose-assembly tail of PoseEstimator._estimate_rotation (process_pose.py:211-239)
+    for the three output heads, computed with the reference's own decoders (bpc/pose/models/losses.py:26-84).
+    The network itself is replaced by recorded raw outputs (the reference hard-codes .to('cuda'), :210)."""
+    import torch
+    import bpc.pose.models.losses as L
+    from bpc_baseline_b200 import synth
+    rng = np.random.default_rng([synth.SEED, 77])
+    n = 48
+    blob = {}
+    # world -> camera rotations with float32-rounded entries widened to float64, as Capture holds them
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    x, y, z, w = q.T
+    Rc = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)], 1),
+                   np.stack([2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)], 1),
+                   np.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], 1)], 1)
+    Rc = Rc.astype(np.float32).astype(np.float64)
+    t = rng.normal(size=(n, 3)) * 500.0
+    blob['cam_R'] = Rc
+    blob['t'] = t
+    raws = {'euler': (rng.normal(size=(n, 3)) * 4.0).astype(np.float32),           # beyond +-pi: the wrap of :215 matters
+            'quat': (rng.normal(size=(n, 4)) * rng.uniform(0.01, 10.0, (n, 1))).astype(np.float32),
+            '6d': rng.normal(size=(n, 6)).astype(np.float32)}
+    for mode, raw in raws.items():
+        finals, poses = [], []
+        for r in range(n):
+            raw_pred = raw[r]
+            if mode == 'euler':                                    # :213-217
+                wrapped_pred = ((raw_pred + np.pi) % (2 * np.pi)) - np.pi
+                euler_tensor = torch.tensor(wrapped_pred, dtype=torch.float32).unsqueeze(0)
+                rot_mat = L.rotmat_from_euler(euler_tensor).squeeze(0).numpy()
+            elif mode == 'quat':                                   # :218-223
+                quat_tensor = torch.tensor(raw_pred, dtype=torch.float32).unsqueeze(0)
+                quat_tensor = quat_tensor / (quat_tensor.norm(dim=1, keepdim=True) + 1e-8)
+                rot_mat = L.quat_to_rotmat(quat_tensor).squeeze(0).numpy()
+            else:                                                  # :224-227
+                rep6d_tensor = torch.tensor(raw_pred, dtype=torch.float32).unsqueeze(0)
+                rot_mat = L.rotmat_from_6d(rep6d_tensor).squeeze(0).numpy()
+            final_rot = Rc[r].T @ rot_mat                          # :233
+            finals.append(final_rot)
+            poses.append(ref.du.calc_pose_matrix(final_rot, t[r]))  # :239
+        blob[f'raw_{mode}'] = raw
+        blob[f'final_{mode}'] = np.stack(finals)
+        blob[f'pose_{mode}'] = np.stack(poses)
+    np.savez_compressed(os.path.join(GOLDEN, 'rotation.npz'), **blob)
+    print(f'  rotation: {n} raw outputs per head (euler, quat, 6d)')
+
+
 def main():
     if not os.path.isdir(REFERENCE):
         raise SystemExit('needs /root/reference (authoring container only)')
@@ -283,7 +332,7 @@ def main():
     ref = import_reference()
     only = set(sys.argv[1:])
     for name, fn in (('geometry', golden_geometry), ('bop_scene', golden_bop_scene), ('crops', golden_crops),
-                     ('dataset', golden_dataset)):
+                     ('dataset', golden_dataset), ('rotation', golden_rotation)):
         if not only or name in only:
             print(name)
             fn(ref)

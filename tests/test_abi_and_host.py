@@ -169,3 +169,22 @@ def test_bop_directory_io(tmp_path):
     assert [im.shape for im in cap.images] == [(8, 9, 3)] * 3 and int(cap.images[2][0, 0, 0]) == 20
     assert all(k.dtype == np.float32 for k in cap.Ks) and all(rt.dtype == np.float64 and rt.shape == (4, 4) for rt in cap.RTs)
     assert cap.RTs[1][2, 3] == 6.125 and cap.gt_poses.shape == (1, 4, 4)
+
+
+def test_rotation_decode_and_pose_assembly_match_reference():
+    """Tail of _estimate_rotation (process_pose.py:211-239) against tests/golden/rotation.npz, which was produced with
+    the reference's own decoders (bpc/pose/models/losses.py) and calc_pose_matrix: host code, no GPU involved."""
+    import torch
+    from bpc_baseline_b200.inference.process_pose import decode_rotations
+    from bpc_baseline_b200.utils.data_utils import calc_pose_matrix
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'rotation.npz'))
+    for mode in ('euler', 'quat', '6d'):
+        raw = torch.from_numpy(g[f'raw_{mode}'])
+        rot = decode_rotations(raw, mode)
+        assert np.array_equal(decode_rotations(raw, None), rot)            # head inferred from the output width
+        for r in range(len(rot)):
+            final = g['cam_R'][r].T @ rot[r]                                   # :233
+            assert np.allclose(final, g[f'final_{mode}'][r], rtol=0, atol=2e-6), (mode, r)
+            assert np.allclose(calc_pose_matrix(final, g['t'][r]), g[f'pose_{mode}'][r], rtol=0, atol=1e-3)
+        # batched decode == the reference's one-at-a-time decode, to float32 rounding of the batched torch ops
+        assert np.abs(np.stack([g['cam_R'][r].T @ rot[r] for r in range(len(rot))]) - g[f'final_{mode}']).max() < 2e-6
