@@ -14,14 +14,16 @@
 //                     float64 arithmetic is left in the hot kernel;
 //   bpc_crop_warp     persistent CTAs; the unit of work is (ROI, strip of 32 output columns), taken by ONE
 //                     WARP from a global atomic counter, plus one "padding" item per ROI.  A warp stages the
-//                     ~130-byte source segments its strip needs with 16-byte cp.async into its own
-//                     double-buffered slice of shared memory and streams down its strip, one lane per
-//                     column: the horizontal pass of a source row is computed once and reused by the two
+//                     ~130-byte source segments its strip needs into its own slice of shared memory with TMA
+//                     (2-D tensor-map boxes of four rows when the image pitch is a multiple of 16 bytes, else one
+//                     1-D bulk copy per row; completion on per-warp mbarriers) and streams down its strip, one
+//                     lane per column: the horizontal pass of a source row is computed once and reused by the
 //                     output rows that tap it.  No CTA barrier, no idle warps behind a narrow letterbox.
-//                     Handles regime 1 with scale < 2 on both axes (<= 3 taps per axis) and regime 3, i.e.
-//                     every box whose long side is below 2T;
-//   bpc_crop_generic  persistent CTAs over the (rare) remaining ROIs: any scale, any regime, source rows
-//                     streamed through shared memory in chunks (handles boxes as large as the image).
+//                     Classes: 1 = regime 1 with scale < 2 on both axes (<= 3 taps per axis, double-buffered
+//                     batches of output rows) and scale exactly 1; 3 = regime 3 (same batches); 4 = regime 1
+//                     with 4..6 taps per axis (2 <= scale <= 5; source rows stream through a four-slot ring);
+//   bpc_crop_generic  persistent CTAs over the (rare) remaining ROIs (class 2): integer ratios >= 2, scale > 5,
+//                     source rows streamed through shared memory in chunks (boxes as large as the image).
 // The dominant traffic is the float32 output (3*T*T*4 B per ROI): each warp stores 128 contiguous bytes per
 // plane and row; padding rows are written with 16-byte stores.
 #include <cuda.h>
