@@ -38,7 +38,7 @@ def stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
-    cmd = [nvcc_path(), '-shared', '-Xcompiler', '-fPIC', '-O3', '-std=c++17', '-lineinfo', '--fmad=false',
+    cmd = [nvcc_path(), '-shared', '-Xcompiler', '-fPIC', '-O3', '-std=c++17', '-lineinfo', '--fmad=false', '--threads', '4',
            *ARCH, '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
     if verbose:
         cmd += ['-Xptxas', '-v']
