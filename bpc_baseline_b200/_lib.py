@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libbpc_b200.so')
+LIB_PATH = os.environ.get('BPC_LIB') or os.path.join(HERE, 'libbpc_b200.so')      # BPC_LIB: experiment builds
 
 _p = C.c_void_p
 _i = C.c_int
@@ -20,10 +20,11 @@ SIGNATURES = {
     'bpc_launch_count': (C.c_ulonglong, []),
     'bpc_fundamental': (_i, [_p, _p, _i, _p, _p]),
     'bpc_cost_tensor': (_i, [_p, _p, _p, _i, _i, _p, _p]),
-    'bpc_match_objects_workspace_bytes': (_sz, [_i, _i, _i, _i]),
-    'bpc_match_objects': (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _p, _sz, _p]),
+    'bpc_match_objects': (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _p]),
     'bpc_match_workspace_bytes': (_sz, [_i, _i]),
-    'bpc_match_triangulate': (_i, [_p, _p, _p, _p, _i, _i, _f, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    'bpc_match_triangulate': (_i, [_p, _p, _p, _p, _i, _i, _f, _i, C.c_double, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    'bpc_pack_records_bytes': (_sz, [_i, _i]),
+    'bpc_pack_records': (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p]),
     'bpc_triangulate': (_i, [_p, _p, _i, _p, _p]),
     'bpc_projection': (_i, [_p, _p, _i, _p, _p]),
     'bpc_reprojection_error': (_i, [_p, _p, _p, _i, _p, _p]),
@@ -34,7 +35,7 @@ SIGNATURES = {
     'bpc_detections_from_yolo': (_i, [_p, _p, _p, _p, _i, _i, _f, _i, _p, _p, _p, _p]),
     'bpc_build_rois': (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     'bpc_train_rois': (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p]),
-    'bpc_roi_crop_workspace_bytes': (_sz, [_i]),
+    'bpc_roi_crop_workspace_bytes': (_sz, [_i, _i]),
     'bpc_roi_crop': (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
     'bpc_roi_crop_u8': (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),
     'bpc_normalise_lut': (_i, [_p, _p, _p, _p]),
@@ -42,6 +43,7 @@ SIGNATURES = {
 }
 
 _lib = None
+ABI_VERSION = 2
 
 
 class BpcError(RuntimeError):
@@ -61,8 +63,8 @@ def load():
         fn = getattr(lib, name)            # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.bpc_abi_version() != 1:
-        raise BpcError(f'ABI version mismatch: library {lib.bpc_abi_version()}, binding 1')
+    if lib.bpc_abi_version() != ABI_VERSION:
+        raise BpcError(f'ABI version mismatch: library {lib.bpc_abi_version()}, binding {ABI_VERSION}')
     _lib = lib
     return lib
 

@@ -121,13 +121,34 @@ def match_objects(cost: torch.Tensor, threshold) -> tuple[torch.Tensor, torch.Te
     n = torch.empty((S,), dtype=torch.int32, device=cost.device)
     with torch.cuda.device(cost.device):
         _lib.check(_lib.load().bpc_match_objects(_p(cost), S, N, M, P, float(np.float32(threshold)), _p(idx), _p(n),
-                                                 None, 0, _stream(cost.device)), 'bpc_match_objects')
+                                                 _stream(cost.device)), 'bpc_match_objects')
     return idx, n
 
 
+_MATCH_WS: dict = {}
+
+
+def _match_workspace(dev, S: int, D: int) -> Optional[torch.Tensor]:
+    """Scratch for scenes too large for shared memory (Dmax above ~450); None below that.  Cached per (device, stream)."""
+    need = int(_lib.load().bpc_match_workspace_bytes(int(S), int(D)))
+    if need == 0:
+        return None
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), int(torch.cuda.current_stream(dev).cuda_stream))
+    ws = _MATCH_WS.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+        _MATCH_WS[key] = ws
+    return ws
+
+
 def match_triangulate(Ks: torch.Tensor, RTs: torch.Tensor, centers: torch.Tensor, counts: torch.Tensor,
-                      threshold=30, want_reproj: bool = True, want_F: bool = False) -> MatchResult:
-    """PoseEstimator._match (process_pose.py:144-188) for S scenes in one launch."""
+                      threshold=30, want_reproj: bool = True, want_F: bool = False,
+                      reproj_thresh: Optional[float] = None) -> MatchResult:
+    """PoseEstimator._match (process_pose.py:144-188) for S scenes in one launch.
+
+    ``reproj_thresh`` (pixels, default None = the reference's behaviour): drop every match whose reprojection error
+    (utils/triangulation.py:14-18) exceeds it in any view; the survivors keep their order.  ``n`` is negative for a
+    scene SciPy would reject (-1) or whose counts exceed Dmax (-2): see :func:`check_match_status`."""
     _chk(Ks, torch.float32, 'Ks', 4); _chk(RTs, torch.float64, 'RTs', 4)
     _chk(centers, torch.float64, 'centers', 4); _chk(counts, torch.int32, 'counts', 2)
     S, _, D, _ = centers.shape
@@ -139,13 +160,55 @@ def match_triangulate(Ks: torch.Tensor, RTs: torch.Tensor, centers: torch.Tensor
     n = torch.empty((S,), dtype=torch.int32, device=dev)
     cost = torch.empty((S, D), dtype=torch.float32, device=dev)
     X = torch.empty((S, D, 3), dtype=torch.float64, device=dev)
-    reproj = torch.empty((S, D, 3), dtype=torch.float64, device=dev) if want_reproj else None
+    reproj = torch.empty((S, D, 3), dtype=torch.float64, device=dev) if (want_reproj or reproj_thresh is not None) else None
     F = torch.empty((S, 3, 3, 3), dtype=torch.float64, device=dev) if want_F else None
     with torch.cuda.device(dev):
+        ws = _match_workspace(dev, S, D)
         _lib.check(_lib.load().bpc_match_triangulate(
             _p(Ks), _p(RTs), _p(centers), _p(counts), S, D, float(np.float32(threshold)),
-            _p(idx), _p(n), _p(cost), _p(X), _p(reproj), _p(F), None, 0, _stream(dev)), 'bpc_match_triangulate')
+            int(reproj_thresh is not None), float(reproj_thresh) if reproj_thresh is not None else 0.0,
+            _p(idx), _p(n), _p(cost), _p(X), _p(reproj), _p(F), _p(ws), ws.numel() if ws is not None else 0, _stream(dev)),
+            'bpc_match_triangulate')
     return MatchResult(idx, n, cost, X, reproj, F)
+
+
+N_INFEASIBLE, N_OVERFLOW = -1, -2        # BPC_N_INFEASIBLE, BPC_N_OVERFLOW
+
+
+def check_match_status(n: torch.Tensor) -> None:
+    """Raise for the per-scene status values of ``MatchResult.n`` (synchronises): ValueError where SciPy raises, RuntimeError
+    where a camera's count exceeds Dmax (e.g. the overflow count of :func:`detections_from_yolo`)."""
+    lo = int(n.min().item()) if n.numel() else 0
+    if lo == N_OVERFLOW:
+        bad = torch.nonzero(n == N_OVERFLOW).flatten()[:8].tolist()
+        raise RuntimeError(f'detection counts exceed Dmax in scenes {bad}: raise Dmax (detections were truncated)')
+    if lo < 0:
+        raise ValueError('matrix contains invalid numeric entries')
+
+
+def pack_records(res: MatchResult, scene_offset: Optional[torch.Tensor] = None, offset_div: int = 3,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The valid matches of every scene as compact 64-byte pose records in one uint8 buffer (see bpc_pack_records in
+    bpc_b200.h): header | n[S] | records (idx i32 x3, cost f32, X f64 x3, reproj f64 x3).  ``scene_offset`` = the
+    exclusive prefix sum from :func:`build_rois` (``offset_div`` 3); computed here if absent."""
+    S, K, _ = res.idx.shape
+    dev = res.idx.device
+    if scene_offset is None:
+        scene_offset = torch.zeros((S + 1,), dtype=torch.int32, device=dev)
+        scene_offset[1:] = torch.cumsum(res.n.clamp(min=0), 0).to(torch.int32)
+        offset_div = 1
+    _chk(scene_offset, torch.int32, 'scene_offset', 1)
+    nbytes = int(_lib.load().bpc_pack_records_bytes(S, K))
+    if out is None:
+        out = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    else:
+        _chk(out, torch.uint8, 'out', 1)
+        if out.numel() < nbytes:
+            raise RuntimeError(f'out must hold {nbytes} bytes')
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().bpc_pack_records(_p(res.idx), _p(res.n), _p(res.cost), _p(res.X), _p(res.reproj), _p(scene_offset),
+                                                int(offset_div), S, K, _p(out), _stream(dev)), 'bpc_pack_records')
+    return out
 
 
 def triangulate(P: torch.Tensor, pts: torch.Tensor) -> torch.Tensor:
@@ -257,13 +320,14 @@ def normalise_lut(device, mean: Sequence[float] = MEAN, std: Sequence[float] = S
 
 _WS_CACHE: dict = {}
 MAX_ROIS_PER_LAUNCH = 32768
+MAX_TARGET = 1024              # BPC_MAX_TARGET
 
 
-def _crop_workspace(dev, R: int) -> torch.Tensor:
+def _crop_workspace(dev, R: int, T: int) -> torch.Tensor:
     """Device scratch for the crop kernels, cached per (device, stream) and grown on demand.
 
     Keyed by the current stream as well: two streams cropping concurrently must not share tap descriptors."""
-    need = int(_lib.load().bpc_roi_crop_workspace_bytes(int(R)))
+    need = int(_lib.load().bpc_roi_crop_workspace_bytes(int(R), int(T)))
     key = (dev.index if dev.index is not None else torch.cuda.current_device(), int(torch.cuda.current_stream(dev).cuda_stream))
     ws = _WS_CACHE.get(key)
     if ws is None or ws.numel() < need:
@@ -277,8 +341,8 @@ def _crop_args(images, rois, T, fill):
     B, H, W, ch = images.shape
     if ch != 3 or rois.shape[1] != 5:
         raise RuntimeError('images must be [B,H,W,3] and rois [R,5]')
-    if not 1 <= int(T) <= 256:
-        raise RuntimeError('target size must be in 1..256')
+    if not 1 <= int(T) <= MAX_TARGET:
+        raise RuntimeError(f'target size must be in 1..{MAX_TARGET}')
     f = (C.c_uint8 * 3)(*[int(v) for v in fill])
     return B, H, W, rois.shape[0], f
 
@@ -307,7 +371,7 @@ def roi_crop(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(255, 
         _chk(status, torch.int32, 'status', 1)
     if n_rois is not None:
         _chk(n_rois, torch.int32, 'n_rois')
-    ws = _crop_workspace(dev, min(R, MAX_ROIS_PER_LAUNCH))
+    ws = _crop_workspace(dev, min(R, MAX_ROIS_PER_LAUNCH), T)
     with torch.cuda.device(dev):
         for lo in range(0, R, MAX_ROIS_PER_LAUNCH):          # bounds the scratch (8.3 KB of tap descriptors per ROI)
             r = min(MAX_ROIS_PER_LAUNCH, R - lo)
@@ -328,7 +392,7 @@ def roi_crop_u8(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(25
         out = torch.empty((R, T, T, 3), dtype=torch.uint8, device=dev)
     if status is not None:
         _chk(status, torch.int32, 'status', 1)
-    ws = _crop_workspace(dev, min(R, MAX_ROIS_PER_LAUNCH))
+    ws = _crop_workspace(dev, min(R, MAX_ROIS_PER_LAUNCH), T)
     with torch.cuda.device(dev):
         for lo in range(0, R, MAX_ROIS_PER_LAUNCH):
             r = min(MAX_ROIS_PER_LAUNCH, R - lo)

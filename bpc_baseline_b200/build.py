@@ -35,20 +35,22 @@ def stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """``defines`` / ``out``: experiment builds (e.g. -DBPC_STG_CS into another file, selected with BPC_LIB)."""
+    if not force and not stale() and out == LIB:
         return LIB
     cmd = [nvcc_path(), '-shared', '-Xcompiler', '-fPIC', '-O3', '-std=c++17', '-lineinfo', '--fmad=false', '--threads', '4',
            *ARCH, '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
     if verbose:
         cmd += ['-Xptxas', '-v']
-    cmd += [os.path.join(CSRC, f) for f in SOURCES] + ['-o', LIB]
+    cmd += [f'-D{d}' for d in defines]
+    cmd += [os.path.join(CSRC, f) for f in SOURCES] + ['-o', out]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError('nvcc failed building libbpc_b200.so')
-    return LIB
+    return out
 
 
 if __name__ == '__main__':

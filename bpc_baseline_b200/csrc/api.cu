@@ -2,7 +2,7 @@
 #include "common.cuh"
 
 namespace bpc {
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0};
 }
 
 extern "C" int bpc_abi_version(void) { return BPC_ABI_VERSION; }
@@ -20,4 +20,4 @@ extern "C" const char* bpc_error_string(int code) {
     return "unknown error";
 }
 
-extern "C" unsigned long long bpc_launch_count(void) { return bpc::g_launches; }
+extern "C" unsigned long long bpc_launch_count(void) { return bpc::g_launches.load(std::memory_order_relaxed); }

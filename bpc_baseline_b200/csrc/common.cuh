@@ -9,15 +9,17 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "bpc_b200.h"
 
 namespace bpc {
 
-extern unsigned long long g_launches;   // host-side launch counter (api.cu)
+extern std::atomic<unsigned long long> g_launches;   // host-side launch counter (api.cu)
 
 #define BPC_LAUNCH_CHECK()                                  \
     do {                                                    \
-        ++::bpc::g_launches;                                \
+        ::bpc::g_launches.fetch_add(1, std::memory_order_relaxed); \
         cudaError_t e__ = cudaGetLastError();               \
         if (e__ != cudaSuccess) return (int)e__;            \
     } while (0)

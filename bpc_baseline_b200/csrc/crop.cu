@@ -28,6 +28,7 @@
 // plane and row; padding rows are written with 16-byte stores.
 #include <cuda.h>
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -41,11 +42,19 @@ constexpr int CROP_BAND = 8;                 // generic kernel: output rows per 
 constexpr int CROP_RAW_BYTES = 40 * 1024;    // generic kernel: staged source bytes
 constexpr int WARP_BUF = 3584;               // warp kernel: bytes of one staging buffer (two per warp)
 constexpr int WARP_DESC = 32 * 16;           // warp kernel: 32 row descriptors (two rings per warp)
-constexpr int WARP_SMEM = 8320;              // 2 staging buffers + 2 descriptor rings + four mbarriers, padded to a multiple of 128
-static_assert(WARP_SMEM % 128 == 0 && WARP_SMEM >= 2 * WARP_BUF + 2 * WARP_DESC + 32 && WARP_BUF % 128 == 0, "TMA box destinations are 128-byte aligned");
+constexpr int WARP_SMEM = 8320;              // 2 staging buffers + 2 descriptor rings + eight mbarriers, padded to a multiple of 128
+static_assert(WARP_SMEM % 128 == 0 && WARP_SMEM >= 2 * WARP_BUF + 2 * WARP_DESC + 64 && WARP_BUF % 128 == 0, "TMA box destinations are 128-byte aligned");
 constexpr int WARPK_WARPS = 8;
-constexpr int WARPK_SMEM = WARPK_WARPS * WARP_SMEM + 768 * 4;
-constexpr int DESC_STRIDE = 256;             // descriptors per ROI and axis (T <= 256)
+constexpr int LUT_STRIDE = 257;              // shared-memory LUT: 256 entries + the normalised fill value per output channel
+constexpr int LUT_SMEM = 3200;               // 3 * 257 floats, padded to a multiple of 128 (TMA destinations follow)
+constexpr int WARPK_SMEM = WARPK_WARPS * WARP_SMEM + LUT_SMEM;
+constexpr int STREAM_ROWS = 8;               // streaming class-1 path: source rows per ring slot (= one TMA box)
+constexpr int STREAM_MAX_PITCH = 288;        // widest staging pitch of a class-1 strip (32 columns at scale < 2 need <= 256)
+constexpr int YSRC_PAD = 16;                 // per-source-row table: zero entries behind the last row (whole slots run to completion)
+static_assert(LUT_SMEM % 128 == 0 && LUT_SMEM >= 3 * LUT_STRIDE * 4, "LUT block");
+// descriptors per ROI: x axis ds float4, y axis ds + 8 float4 (class 1 reads the y block as 2*ds + 16 float2 source-row records),
+// ds = T rounded up to 32
+__host__ __device__ __forceinline__ int desc_stride(int T) { return (T + 31) & ~31; }
 
 struct RoiGeom {                             // 88 bytes, workspace
     double scale_x, scale_y, inv_x, inv_y;
@@ -63,7 +72,8 @@ static_assert(sizeof(RoiGeom) == 88, "RoiGeom layout");
 // source rows of a strip instead of one bulk copy per row; rows / columns beyond the pool are zero-filled by the TMA
 // unit, which removes the guarded tail path.
 constexpr int N_TMAPS = 15;
-struct TmapSet { CUtensorMap m[N_TMAPS]; };
+constexpr int N_TMAPS8 = 8;                  // 8-row boxes for the streaming class-1 path: pitches 64 .. 288
+struct TmapSet { CUtensorMap m[N_TMAPS]; CUtensorMap m8[N_TMAPS8]; };
 __host__ __device__ __forceinline__ int tmap_pitch(int need) { return need <= 448 ? (need < 64 ? 64 : ((need + 31) & ~31)) : ((need + 63) & ~63); }
 __host__ __device__ __forceinline__ int tmap_index(int pitch) { return pitch <= 448 ? (pitch - 64) / 32 : 13 + (pitch - 512) / 64; }
 __host__ __device__ __forceinline__ int tmap_rows(int pitch) { return pitch <= 448 ? 4 : 2; }
@@ -149,19 +159,27 @@ __device__ __forceinline__ void linear_coef(int d, double scale, double inv, int
 // ------------------------------------------------------------------------------------------------------
 // prep: geometry, classification and tap descriptors, one CTA per ROI
 // ------------------------------------------------------------------------------------------------------
-// Descriptor formats (float4, DESC_STRIDE per ROI and axis):
+// Descriptor formats (float4; desc_stride(T) per ROI on the x axis, desc_stride(T) + 8 on the y axis):
 //   class 1 (area, <= 3 taps)  x: (w0, w1, w2, bits(first source column))
-//                              y: (b0, b1, b2, bits(first source row | taps << 24))
+//                              y: (b0, b1, b2, bits(first source row | taps << 24))          [image pitch not a multiple of 16]
+//                              y: float2 per SOURCE row s (the streaming path): (ba, bb).  |ba| = weight of row s in the
+//                                 output row being accumulated; sign bit of ba set = that output row is complete after row s;
+//                                 bb = weight of row s as the first tap of the next output row (+0 if it has none there).
+//                                 An output row then is acc = (((0 + b0 h0) + b1 h1) + b2 h2), bit-identical to OpenCV's
+//                                 sum = b0 h0; sum += b1 h1; ... for non-negative terms.
 //   class 3 (fixed-point)      x: (bits(w0), bits(w1), 0, bits(source column))      w = 2048, 0 beyond xmax
 //                              y: (bits(b0), bits(b1), bits(second source row), bits(first source row))
 __global__ void __launch_bounds__(256)
 bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const int32_t* __restrict__ rois, int R,
-                     const int32_t* __restrict__ n_rois_dev, int roi_first, int T,
+                     const int32_t* __restrict__ n_rois_dev, int roi_first, int T, int stream_ok,
                      RoiGeom* __restrict__ geom, float4* __restrict__ xdesc, float4* __restrict__ ydesc,
                      int32_t* __restrict__ glist, int32_t* __restrict__ gcount, int32_t* __restrict__ status) {
     __shared__ RoiGeom g;
+    __shared__ int s_bad;
     const int roi = blockIdx.x, tid = threadIdx.x;
+    const int ds = desc_stride(T);
     if (tid == 0) {
+        s_bad = 0;
         g.scale_x = g.scale_y = g.inv_x = g.inv_y = 0.0;
         g.src = 0ull;
         g.new_w = g.new_h = g.dx = g.dy = 0;
@@ -210,51 +228,79 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                 }
             }
             if (status != nullptr) status[roi] = (g.regime == 0) ? 1 : 0;
-            if (g.cls == 2) glist[atomicAdd(gcount, 1)] = roi;
         }
-        geom[roi] = g;
     }
     __syncthreads();
     const int cls = g.cls;
-    if (cls != 1 && cls != 3 && cls != 4) return;
-    float4* xd = xdesc + (size_t)roi * DESC_STRIDE;
-    float4* yd = ydesc + (size_t)roi * DESC_STRIDE;
+    float4* xd = xdesc + (size_t)roi * ds;
+    float4* yd = ydesc + (size_t)roi * (ds + 8);
     if (cls == 4) {
         // (w_first, w_middle, w_last, bits(start | taps << 24)); a missing first / last tap takes the middle weight
         for (int axis = 0; axis < 2; ++axis) {
             const int nd = axis ? g.new_h : g.new_w;
-            if (tid < nd) {
+            for (int d = tid; d < nd; d += 256) {
                 int st, n, flags; float af, am, al;
-                area_taps(tid, axis ? g.scale_y : g.scale_x, axis ? g.h : g.w, st, n, af, am, al, flags);
+                area_taps(d, axis ? g.scale_y : g.scale_x, axis ? g.h : g.w, st, n, af, am, al, flags);
                 const float w0 = (flags & 1) ? af : ((n == 1 && (flags & 2)) ? al : am);
                 const float wl = (flags & 2) ? al : am;
-                (axis ? yd : xd)[tid] = make_float4(w0, am, wl, __int_as_float(st | (n << 24)));
+                (axis ? yd : xd)[d] = make_float4(w0, am, wl, __int_as_float(st | (n << 24)));
             }
         }
     } else if (cls == 1) {
-        if (tid < g.new_w) {
+        for (int d = tid; d < g.new_w; d += 256) {
             int xs, xn; float w0, w1, w2;
-            area_taps3(tid, g.scale_x, g.w, xs, xn, w0, w1, w2);
-            xd[tid] = make_float4(w0, w1, w2, __int_as_float(xs));
+            area_taps3(d, g.scale_x, g.w, xs, xn, w0, w1, w2);
+            xd[d] = make_float4(w0, w1, w2, __int_as_float(xs));
         }
-        if (tid < g.new_h) {
-            int ys, yn; float b0, b1, b2;
-            area_taps3(tid, g.scale_y, g.h, ys, yn, b0, b1, b2);
-            yd[tid] = make_float4(b0, b1, b2, __int_as_float(ys | (yn << 24)));
+        if (!stream_ok) {
+            for (int d = tid; d < g.new_h; d += 256) {
+                int ys, yn; float b0, b1, b2;
+                area_taps3(d, g.scale_y, g.h, ys, yn, b0, b1, b2);
+                yd[d] = make_float4(b0, b1, b2, __int_as_float(ys | (yn << 24)));
+            }
+        } else {
+            // per-source-row records; rows [h, hpad) stay zero (no contribution, no completed row)
+            float2* ysrc = reinterpret_cast<float2*>(yd);
+            const int hpad = min(2 * ds + YSRC_PAD, ((g.h + STREAM_ROWS - 1) / STREAM_ROWS) * STREAM_ROWS + STREAM_ROWS);
+            if (g.h + STREAM_ROWS > 2 * ds + YSRC_PAD) s_bad = 1;            // cannot happen for scale_y < 2 (h < 2 T)
+            for (int s = tid; s < hpad; s += 256) ysrc[s] = make_float2(0.f, 0.f);
+            __syncthreads();
+            for (int d = tid; d < g.new_h && !s_bad; d += 256) {
+                int ys, yn, pys = 0, pyn = 0; float b[3], pb[3];
+                area_taps3(d, g.scale_y, g.h, ys, yn, b[0], b[1], b[2]);
+                if (d > 0) area_taps3(d - 1, g.scale_y, g.h, pys, pyn, pb[0], pb[1], pb[2]);
+                const int prev_last = d > 0 ? pys + pyn - 1 : -1;
+                if (yn < 1 || yn > 3 || ys < prev_last || ys + yn > g.h) { s_bad = 1; break; }
+                for (int t = 0; t < yn; ++t) {
+                    const int s = ys + t;
+                    const bool shared_first = (t == 0 && s == prev_last);       // row s also closes output row d - 1
+                    if (shared_first && yn == 1) { s_bad = 1; break; }          // one source row closing two output rows: generic path
+                    float wv = b[t];
+                    if (t == yn - 1) wv = __int_as_float(__float_as_int(wv) | (int)0x80000000u);
+                    if (shared_first) ysrc[s].y = wv; else ysrc[s].x = wv;
+                }
+            }
+            __syncthreads();
+            if (s_bad && tid == 0) { g.cls = 2; }
         }
-    } else {
-        if (tid < g.new_w) {
+    } else if (cls == 3) {
+        for (int d = tid; d < g.new_w; d += 256) {
             int xs, w0, w1, edge;
-            linear_coef(tid, g.scale_x, g.inv_x, g.w, xs, w0, w1, edge);
+            linear_coef(d, g.scale_x, g.inv_x, g.w, xs, w0, w1, edge);
             if (edge) { w0 = 2048; w1 = 0; }                        // D = S[sx] * ONE beyond xmax
-            xd[tid] = make_float4(__int_as_float(w0), __int_as_float(w1), 0.f, __int_as_float(xs));
+            xd[d] = make_float4(__int_as_float(w0), __int_as_float(w1), 0.f, __int_as_float(xs));
         }
-        if (tid < g.new_h) {
+        for (int d = tid; d < g.new_h; d += 256) {
             int s0, b0, b1, edge;
-            linear_coef(tid, g.scale_y, g.inv_y, g.h, s0, b0, b1, edge);
+            linear_coef(d, g.scale_y, g.inv_y, g.h, s0, b0, b1, edge);
             const int s1 = min(s0 + 1, g.h - 1);
-            yd[tid] = make_float4(__int_as_float(b0), __int_as_float(b1), __int_as_float(s1), __int_as_float(s0));
+            yd[d] = make_float4(__int_as_float(b0), __int_as_float(b1), __int_as_float(s1), __int_as_float(s0));
         }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (g.cls == 2) glist[atomicAdd(gcount, 1)] = roi;
+        geom[roi] = g;
     }
 }
 
@@ -264,7 +310,7 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
 template <bool OUT_U8>
 struct Out {
     float* outf; uint8_t* outb;
-    const float* lut;           // shared memory [768]
+    const float* lut;           // shared memory [3][LUT_STRIDE]
     int T, swap_rb;
     uint8_t fillc[3];
     float padf[3];
@@ -277,8 +323,8 @@ struct Out {
             const int s0 = swap_rb ? b2 : b0, s2 = swap_rb ? b0 : b2;
             float* o = outf + ((size_t)roi * 3 * T + y) * T + x;
             o[0] = lut[s0];
-            o[(size_t)T * T] = lut[256 + b1];
-            o[(size_t)2 * T * T] = lut[512 + s2];
+            o[(size_t)T * T] = lut[LUT_STRIDE + b1];
+            o[(size_t)2 * T * T] = lut[2 * LUT_STRIDE + s2];
         }
     }
     __device__ __forceinline__ void pad(int roi, int y, int x) const {
@@ -319,7 +365,7 @@ __device__ __forceinline__ void out_init(Out<OUT_U8>& o, float* outf, uint8_t* o
     o.outf = outf; o.outb = outb; o.lut = lut_s; o.T = T; o.swap_rb = swap_rb;
     o.fillc[0] = fill.x; o.fillc[1] = fill.y; o.fillc[2] = fill.z;
     if (!OUT_U8)
-        for (int p = 0; p < 3; ++p) o.padf[p] = lut_s[p * 256 + o.fillc[swap_rb ? 2 - p : p]];
+        for (int p = 0; p < 3; ++p) o.padf[p] = lut_s[p * LUT_STRIDE + o.fillc[swap_rb ? 2 - p : p]];
 }
 
 
@@ -367,6 +413,15 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
+}
+
+// output store of the fast paths: the crop buffer is written once and never re-read by this kernel
+__device__ __forceinline__ void stg_out(float* p, float v) {
+#ifdef BPC_STG_CS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
 }
 
 // horizontal pass of one source row for one output column: 9 bytes starting at shared address a4 + sh/8
@@ -509,23 +564,29 @@ __global__ void __launch_bounds__(256, 3)
 bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom,
                      const float4* __restrict__ xdesc, const float4* __restrict__ ydesc, int32_t* __restrict__ wcount,
                      int R, int Trt, int nslot, uchar4 fill, int swap_rb, const float* __restrict__ lut_g,
-                     float* __restrict__ outf, uint8_t* __restrict__ outb, const __grid_constant__ TmapSet tm) {
+                     float* __restrict__ outf, uint8_t* __restrict__ outb, const __grid_constant__ TmapSet tm, int dbg) {
     extern __shared__ __align__(128) unsigned char smem[];
-    float* lut = reinterpret_cast<float*>(smem);                                 // [768]
+    float* lut = reinterpret_cast<float*>(smem);                                 // [3][LUT_STRIDE]: 256 values + the fill value
     const int T = TT ? TT : Trt;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    unsigned char* wbase = smem + 768 * 4 + wid * WARP_SMEM;          // [2][WARP_BUF] staging, then [2][32] float4 row descriptors
+    unsigned char* wbase = smem + LUT_SMEM + wid * WARP_SMEM;         // [2][WARP_BUF] staging, then [2][32] float4 row descriptors
     const unsigned wbase_s = (unsigned)__cvta_generic_to_shared(wbase), lut_s = (unsigned)__cvta_generic_to_shared(smem);
 
-    const unsigned lut_m = lut_s - 4u * 0x4B000000u;                    // see lut_addr()
-    const unsigned bar_s = wbase_s + 2 * WARP_BUF + 2 * WARP_DESC;     // four mbarriers: one per staging buffer / ring slot
-    if (lane == 0) { mbar_init(bar_s, 1); mbar_init(bar_s + 8, 1); mbar_init(bar_s + 16, 1); mbar_init(bar_s + 24, 1); }
+    // see lut_addr(); passed through shared memory so that it stays ONE register (ptxas otherwise re-derives it as window
+    // base + constant with an extra add per use)
+    if (tid == 0) *reinterpret_cast<volatile unsigned*>(smem + 3 * LUT_STRIDE * 4) = lut_s - 4u * 0x4B000000u;
+    const unsigned bar_s = wbase_s + 2 * WARP_BUF + 2 * WARP_DESC;     // eight mbarriers: one per staging buffer / ring slot
+    if (lane < 8) mbar_init(bar_s + 8 * lane, 1);
     unsigned ph = 0;                                                      // bit j: parity of the next completion of barrier j
     if (!OUT_U8)
-        for (int e = tid; e < 768; e += 256) lut[e] = lut_g[e];
+        for (int e = tid; e < 768; e += 256) lut[(e >> 8) * LUT_STRIDE + (e & 255)] = lut_g[e];
     __syncthreads();
     Out<OUT_U8> out;
     out_init(out, outf, outb, lut, T, swap_rb, fill);
+    if (!OUT_U8 && tid < 3) lut[tid * LUT_STRIDE + 256] = out.padf[tid];  // entry 256 = fill: what a lane beside the image looks up
+    __syncthreads();
+    const unsigned lut_m = *reinterpret_cast<volatile unsigned*>(smem + 3 * LUT_STRIDE * 4);
+    const int ds = desc_stride(T), ystride = ds + 8;
     constexpr bool swap = SWAP;
     const size_t plane = (size_t)T * T;
     const unsigned long long rowstride = (unsigned long long)W * 3ull;
@@ -568,7 +629,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
         const int xr = x - dx0;
         const bool active = xr >= 0 && xr < new_w;
         const bool padlane = !active && x < T;
-        const float4 xd = xdesc[(size_t)roi * DESC_STRIDE + min(max(xr, 0), new_w - 1)];
+        const float4 xd = xdesc[(size_t)roi * ds + min(max(xr, 0), new_w - 1)];
         const int xs = __float_as_int(xd.w) & 0xffffff;
         const int xn = (cls == 4) ? (__float_as_int(xd.w) >> 24) : 3;     // source pixels read from xs on
         const int xs_min = -warp_max_i32(-xs);
@@ -593,7 +654,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
         // bh output rows tap at most bh*scale + 2 source rows; whole TMA boxes round that up by rb - 1 more
         const int bh = max(1, min(32, (int)((double)(rows_fit - (ALIGNED ? 5 : 3)) / (scale_y < 1.0 ? 1.0 : scale_y))));
         const int nb = (new_h + bh - 1) / bh;
-        const float4* ydr = ydesc + (size_t)roi * DESC_STRIDE;
+        const float4* ydr = ydesc + (size_t)roi * ystride;
         float* optr = outf + ((size_t)roi * 3 * T + dy0) * T + x;     // (plane 0, current row, column x)
         const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
@@ -711,8 +772,8 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                         } else {
                             const unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
                             optr[0] = lds_f32(swap ? l2 : l0);
-                            optr[plane] = lds_f32(l1 + 1024);
-                            optr[2 * plane] = lds_f32((swap ? l0 : l2) + 2048);
+                            optr[plane] = lds_f32(l1 + 4 * LUT_STRIDE);
+                            optr[2 * plane] = lds_f32((swap ? l0 : l2) + 8 * LUT_STRIDE);
                             optr += T;
                         }
                     } else if (padlane) {
@@ -727,13 +788,101 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             continue;
         }
 
+        if (ALIGNED && cls == 1) {
+            // ---------------- regime 1, <= 3 taps per axis (scale < 2): source rows stream in order ----------------
+            // Ring of 8-row slots (one 2-D TMA box + the 64 bytes of the eight rows' (ba, bb) records per slot, one mbarrier
+            // each, every slot but the one being read in flight); the horizontal pass of four rows is computed back to back
+            // (12 independent loads), then every row is added to the open output row with weight |ba|; a row whose record
+            // has the sign of ba set closes that output row (LUT, three 128-byte stores) and opens the next one with
+            // weight bb.  No per-output-row tap loop, no tap-count branches, every source row staged exactly once.
+            ColW cw;
+            cw.set(xd.x, xd.y, xd.z);
+            if (!active) {                               // beside the image: every row sums to 256 -> LUT entry 256 = fill
+                cw.w[0] = cw.w[1] = cw.w[2] = 0.f;
+                cw.c[0] = 256.f; cw.c[1] = cw.c[2] = 0.f;
+            }
+            const int nchunks = (gp->h + STREAM_ROWS - 1) / STREAM_ROWS;
+            const unsigned slot_bytes = (unsigned)(STREAM_ROWS * pitch);
+            const int nsl = min(4, (2 * WARP_BUF) / (int)slot_bytes);                   // >= 3 (pitch <= STREAM_MAX_PITCH)
+            const unsigned dring = wbase_s + 2 * WARP_BUF;                              // [4 slots][8 rows] float2
+            const unsigned long long ysrc = (unsigned long long)(uintptr_t)(ydesc + (size_t)roi * ystride);
+            const CUtensorMap* map8 = &tm.m8[min(tmap_index(pitch), N_TMAPS8 - 1)];
+            auto issue = [&](int c, int j) {
+                if (lane == 0) {
+                    mbar_expect_tx(bar_s + 8 * j, slot_bytes + 8u * STREAM_ROWS);
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 :: "r"(wbase_s + (unsigned)j * slot_bytes), "l"(map8), "r"(xw), "r"(row0 + c * STREAM_ROWS), "r"(bar_s + 8 * j) : "memory");
+                    bulk_g2s(dring + 8u * STREAM_ROWS * j, ysrc + 8ull * STREAM_ROWS * c, 8u * STREAM_ROWS, bar_s + 8 * j);
+                }
+            };
+            __syncwarp();                                   // previous item finished with the buffers
+            for (int c = 0; c < min(nsl, nchunks); ++c) issue(c, c);
+            u64 acc01 = 0ull;
+            float acc2 = 0.f;
+            unsigned roff = 0;                                // element offset of the open output row from optr
+            int yout = 0;
+            const bool store_ok = ((TT && TT % 32 == 0) || x < T) && !(dbg & 2);
+            int j = 0;
+            for (int c = 0; c < nchunks; ++c) {
+                mbar_wait(bar_s + 8 * j, (ph >> j) & 1u); ph ^= 1u << j;
+                const unsigned rbase = wbase_s + (unsigned)j * slot_bytes + colc4;
+#pragma unroll
+                for (int half = 0; half < STREAM_ROWS / 4; ++half) {
+                    const float4 dA = lds_f4(dring + 8u * STREAM_ROWS * j + 32u * half), dB = lds_f4(dring + 8u * STREAM_ROWS * j + 32u * half + 16);
+                    u64 h01[4];
+                    float h2[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) h_area3(rbase + (unsigned)((4 * half + k) * pitch), shc, cw, h01[k], h2[k]);
+                    if (half == STREAM_ROWS / 4 - 1) {
+                        __syncwarp();                           // every lane has read slot j: refill it
+                        if (c + nsl < nchunks) issue(c + nsl, j);
+                    }
+                    const float ba[4] = {dA.x, dA.z, dB.x, dB.z}, bb[4] = {dA.y, dA.w, dB.y, dB.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float wa = fabsf(ba[k]);
+                        acc01 = fadd2(acc01, fprod2(pack2(wa, wa), h01[k], nz2));
+                        acc2 = __fadd_rn(acc2, __fmul_rn(wa, h2[k]));
+                        if (__float_as_int(ba[k]) < 0) {            // output row complete
+                            float a0f, a1f;
+                            unpack2(acc01, a0f, a1f);
+                            if (OUT_U8) {
+                                if (active) out.px(roi, dy0 + yout, x, round_u8(a0f), round_u8(a1f), round_u8(acc2));
+                                else if (padlane) out.pad(roi, dy0 + yout, x);
+                                ++yout;
+                            } else if (!(dbg & 4)) {
+                                unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
+                                if (dbg & 1) { l0 = l1 = l2 = lut_s + 4 * lane; }
+                                if (store_ok) {
+                                    float* o = optr + roff;
+                                    if (dbg & 16) o = outf + ((size_t)(o - outf) & (size_t)0x3fffff);     // what-if: L2-resident window
+                                    if (dbg & 8) {                                                        // what-if: no LDS -> STG dependency
+                                        stg_out(o, a0f); stg_out(o + plane, a1f); stg_out(o + 2 * plane, acc2);
+                                    } else {
+                                    stg_out(o, lds_f32(swap ? l2 : l0));
+                                    stg_out(o + plane, lds_f32(l1 + 4 * LUT_STRIDE));
+                                    stg_out(o + 2 * plane, lds_f32((swap ? l0 : l2) + 8 * LUT_STRIDE));
+                                    }
+                                }
+                                roff += (unsigned)T;
+                            }
+                            acc01 = fprod2(pack2(bb[k], bb[k]), h01[k], nz2);
+                            acc2 = __fmul_rn(bb[k], h2[k]);
+                        }
+                    }
+                }
+                j = (j + 1 == nsl) ? 0 : j + 1;
+            }
+            continue;
+        }
+
         __syncwarp();                                   // previous item finished with the buffers
         int s_lo_cur = stage(0, 0, load_desc(0));
         bulk_cur = bulk_next;
         float4 ydn = load_desc(1);
         int s_lo_next = 0;
 
-        if (cls == 1) {
+        if (!ALIGNED && cls == 1) {
             ColW cw;
             cw.set(xd.x, xd.y, xd.z);
             int crow = -1;
@@ -791,8 +940,8 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                             const unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
                             float* o = optr + roff;               // fresh address registers per row: no wait on the previous row's stores
                             o[0] = lds_f32(swap ? l2 : l0);
-                            o[plane] = lds_f32(l1 + 1024);
-                            o[2 * plane] = lds_f32((swap ? l0 : l2) + 2048);
+                            o[plane] = lds_f32(l1 + 4 * LUT_STRIDE);
+                            o[2 * plane] = lds_f32((swap ? l0 : l2) + 8 * LUT_STRIDE);
                             roff += (unsigned)T;
                         }
                     }
@@ -846,8 +995,8 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                             out.px(roi, dy0 + y0 + r, x, o[0], o[1], o[2]);
                         } else {
                             optr[0] = lds_f32(lut_s + 4 * (swap ? o[2] : o[0]));
-                            optr[plane] = lds_f32(lut_s + 1024 + 4 * o[1]);
-                            optr[2 * plane] = lds_f32(lut_s + 2048 + 4 * (swap ? o[0] : o[2]));
+                            optr[plane] = lds_f32(lut_s + 4 * LUT_STRIDE + 4 * o[1]);
+                            optr[2 * plane] = lds_f32(lut_s + 8 * LUT_STRIDE + 4 * (swap ? o[0] : o[2]));
                             optr += T;
                         }
                     }
@@ -1039,20 +1188,20 @@ __device__ void crop_generic_band(unsigned char* raw, YDesc* yd, const Out<OUT_U
     }
 }
 
-template <bool OUT_U8>
-__global__ void __launch_bounds__(256)
+template <bool OUT_U8, int NTH>
+__global__ void __launch_bounds__(NTH)
 bpc_crop_generic_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom,
                         const int32_t* __restrict__ glist, const int32_t* __restrict__ gcount, int T, int nbands,
                         uchar4 fill, int swap_rb, const float* __restrict__ lut_g, float* __restrict__ outf, uint8_t* __restrict__ outb) {
     extern __shared__ __align__(16) unsigned char raw[];
     __shared__ RoiGeom g;
     __shared__ YDesc yd[CROP_BAND];
-    __shared__ float lut[OUT_U8 ? 1 : 768];
+    __shared__ float lut[OUT_U8 ? 1 : 3 * LUT_STRIDE];
     const int tid = threadIdx.x, nth = blockDim.x;
     const long long items = (long long)(*gcount) * nbands;
     if (blockIdx.x >= items) return;
     if (!OUT_U8)
-        for (int e = tid; e < 768; e += nth) lut[e] = lut_g[e];
+        for (int e = tid; e < 768; e += nth) lut[(e >> 8) * LUT_STRIDE + (e & 255)] = lut_g[e];
     __syncthreads();
     Out<OUT_U8> out;
     out_init(out, outf, outb, lut, T, swap_rb, fill);
@@ -1110,46 +1259,55 @@ static int tensor_maps(const uint8_t* images, int B, int H, int W, bool aligned,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { k_images = nullptr; return (int)cudaErrorInvalidValue; }
     }
+    for (int i = 0; i < N_TMAPS8; ++i) {
+        const int pitch = 64 + 32 * i;
+        const cuuint32_t box[2] = {(cuuint32_t)pitch / 4, (cuuint32_t)STREAM_ROWS};
+        const CUresult r = encode(&cached.m8[i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)images, gdim, gstride, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { k_images = nullptr; return (int)cudaErrorInvalidValue; }
+    }
     k_images = images; k_B = B; k_H = H; k_W = W; k_dev = dev;
     *out = cached;
     return BPC_OK;
 }
 
-// workspace: geom[R] | xdesc[R][256] | ydesc[R][256] | counters[16] | glist[R]
+// workspace: geom[R] | xdesc[R][ds] | ydesc[R][ds + 8] | counters[16] | glist[R]      (ds = desc_stride(T), float4 records)
 static size_t ws_off_xdesc(int R) { return (((size_t)R * sizeof(RoiGeom)) + 15) & ~(size_t)15; }
-static size_t ws_off_ydesc(int R) { return ws_off_xdesc(R) + (size_t)R * DESC_STRIDE * sizeof(float4); }
-static size_t ws_off_count(int R) { return ws_off_ydesc(R) + (size_t)R * DESC_STRIDE * sizeof(float4); }
-static size_t crop_workspace_bytes(int R) { return ws_off_count(R) + 64 + (size_t)R * sizeof(int32_t) + 64; }
+static size_t ws_off_ydesc(int R, int T) { return ws_off_xdesc(R) + (size_t)R * desc_stride(T) * sizeof(float4); }
+static size_t ws_off_count(int R, int T) { return ws_off_ydesc(R, T) + (size_t)R * (desc_stride(T) + 8) * sizeof(float4); }
+static size_t crop_workspace_bytes(int R, int T) { return ws_off_count(R, T) + 64 + (size_t)R * sizeof(int32_t) + 64; }
 
 template <bool OUT_U8>
 static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R, const int32_t* n_rois_dev,
                        int roi_first, int T, const uint8_t* fill, int swap_rb, const float* lut, float* outf, uint8_t* outb,
                        int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
-    if (R < 0 || B < 1 || H < 1 || W < 1 || T < 1 || T > 256 || !fill) return BPC_EINVAL;
+    if (R < 0 || B < 1 || H < 1 || W < 1 || T < 1 || T > BPC_MAX_TARGET || !fill) return BPC_EINVAL;
     if (R > 0 && (!images || !rois || !workspace || (!OUT_U8 && (!lut || !outf)) || (OUT_U8 && !outb))) return BPC_EINVAL;
     if (((uintptr_t)images & 15) != 0 || ((uintptr_t)workspace & 15) != 0) return BPC_EALIGN;
     if (R == 0) return BPC_OK;
-    if (workspace_bytes < crop_workspace_bytes(R)) return BPC_EWORKSPACE;
+    if (workspace_bytes < crop_workspace_bytes(R, T)) return BPC_EWORKSPACE;
     const int nslot = (T + 31) / 32 + 1;
     if ((long long)R * nslot > 0x7fffffffLL) return BPC_ETOOBIG;
     cudaStream_t st = (cudaStream_t)stream;
     unsigned char* wsb = (unsigned char*)workspace;
     RoiGeom* geom = (RoiGeom*)wsb;
     float4* xdesc = (float4*)(wsb + ws_off_xdesc(R));
-    float4* ydesc = (float4*)(wsb + ws_off_ydesc(R));
-    int32_t* gcount = (int32_t*)(wsb + ws_off_count(R));      // [0] generic-list length, [4] warp-item counter
+    float4* ydesc = (float4*)(wsb + ws_off_ydesc(R, T));
+    int32_t* gcount = (int32_t*)(wsb + ws_off_count(R, T));   // [0] generic-list length, [4] warp-item counter
     int32_t* wcount = gcount + 4;
     int32_t* glist = gcount + 16;
     cudaError_t e = cudaMemsetAsync(gcount, 0, 64, st);
     if (e != cudaSuccess) return (int)e;
-    bpc_crop_prep_kernel<<<R, 256, 0, st>>>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, geom, xdesc, ydesc, glist, gcount, status);
+    // 2-D TMA staging needs a 16-byte image pitch; rows narrower than the widest box keep the 1-D path
+    const bool aligned = ((long long)W * 3) % 16 == 0 && (long long)W * 3 >= TMAP_MAX_PITCH;
+    bpc_crop_prep_kernel<<<R, 256, 0, st>>>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, aligned ? 1 : 0, geom, xdesc, ydesc,
+                                            glist, gcount, status);
     BPC_LAUNCH_CHECK();
     const uchar4 f4 = make_uchar4(fill[0], fill[1], fill[2], 0);
     {
         typedef void (*WarpFn)(const uint8_t*, int, int, int, const RoiGeom*, const float4*, const float4*, int32_t*, int, int, int,
-                               uchar4, int, const float*, float*, uint8_t*, const TmapSet);
-        // 2-D TMA staging needs a 16-byte image pitch; rows narrower than the widest box keep the 1-D path
-        const bool aligned = ((long long)W * 3) % 16 == 0 && (long long)W * 3 >= TMAP_MAX_PITCH;
+                               uchar4, int, const float*, float*, uint8_t*, const TmapSet, int);
         TmapSet tmaps;
         const int terr = tensor_maps(images, B, H, W, aligned, &tmaps);
         if (terr != BPC_OK) return terr;
@@ -1163,6 +1321,7 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
         else if (T == 256) fn = BPC_PICK(256);
         else fn = BPC_PICK(0);
 #undef BPC_PICK
+        // the same constant on every call: idempotent, so concurrent callers cannot interleave set(small) / launch(large)
         e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, WARPK_SMEM);
         if (e != cudaSuccess) return (int)e;
         const long long nitems = (long long)R * nslot;
@@ -1173,20 +1332,25 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, WARPK_SMEM) != cudaSuccess || per_sm < 1) per_sm = 1;
         const long long slots = (long long)sms * per_sm;
         const int grid = (int)(want < slots ? want : slots);
-        fn<<<grid, 256, WARPK_SMEM, st>>>(images, B, H, W, geom, xdesc, ydesc, wcount, R, T, nslot, f4, swap_rb, lut, outf, outb, tmaps);
+        static const int dbg = getenv("BPC_CROP_DEBUG") ? atoi(getenv("BPC_CROP_DEBUG")) : 0;
+        fn<<<grid, 256, WARPK_SMEM, st>>>(images, B, H, W, geom, xdesc, ydesc, wcount, R, T, nslot, f4, swap_rb, lut, outf, outb, tmaps, dbg);
         BPC_LAUNCH_CHECK();
-    }
-    static bool attr_set[2] = {false, false};
-    if (!attr_set[OUT_U8]) {
-        e = cudaFuncSetAttribute(bpc_crop_generic_kernel<OUT_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROP_RAW_BYTES);
-        if (e != cudaSuccess) return (int)e;
-        attr_set[OUT_U8] = true;
     }
     const int nbands = (T + CROP_BAND - 1) / CROP_BAND;
     const long long max_items = (long long)R * nbands;
     const int grid = (int)(max_items < 148 * 2 ? max_items : 148 * 2);
-    const int threads = ((T + 31) / 32) * 32;
-    bpc_crop_generic_kernel<OUT_U8><<<grid, threads, CROP_RAW_BYTES, st>>>(images, B, H, W, geom, glist, gcount, T, nbands, f4, swap_rb, lut, outf, outb);
+    const int threads = ((T + 31) / 32) * 32;                   // one thread per output column
+    if (threads <= 256) {
+        e = cudaFuncSetAttribute(bpc_crop_generic_kernel<OUT_U8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROP_RAW_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        bpc_crop_generic_kernel<OUT_U8, 256><<<grid, threads, CROP_RAW_BYTES, st>>>(images, B, H, W, geom, glist, gcount, T, nbands, f4,
+                                                                                   swap_rb, lut, outf, outb);
+    } else {
+        e = cudaFuncSetAttribute(bpc_crop_generic_kernel<OUT_U8, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROP_RAW_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        bpc_crop_generic_kernel<OUT_U8, 1024><<<grid, threads, CROP_RAW_BYTES, st>>>(images, B, H, W, geom, glist, gcount, T, nbands, f4,
+                                                                                    swap_rb, lut, outf, outb);
+    }
     BPC_LAUNCH_CHECK();
     return BPC_OK;
 }
@@ -1195,7 +1359,7 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
 
 using namespace bpc;
 
-extern "C" size_t bpc_roi_crop_workspace_bytes(int R) { return R < 0 ? 0 : crop_workspace_bytes(R); }
+extern "C" size_t bpc_roi_crop_workspace_bytes(int R, int T) { return (R < 0 || T < 1 || T > BPC_MAX_TARGET) ? 0 : crop_workspace_bytes(R, T); }
 
 extern "C" int bpc_roi_crop(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R,
                             const int32_t* n_rois_dev, int roi_first, int T, const uint8_t* fill, int swap_rb,

@@ -9,9 +9,13 @@
 namespace bpc {
 
 // ---- float32 inverse of K (np.linalg.inv on a float32 3x3, camera_utils.py:38-39) -------------------
+// numpy.linalg.inv computes in DOUBLE whatever the input type (numpy/linalg/_linalg.py: _commonType returns
+// `double` as the computation type, the 'd->d' gufunc = LAPACK dgesv runs, and the result is cast back with
+// astype(float32)), so the float32 inverse is the correctly rounded exact inverse up to double rounding.
+// Checked against np.linalg.inv: 3000 / 3000 skewed K bit-equal to float32(exact); golden tests/golden/skew.npz.
 __device__ inline void inv3_f32(const float* K, float* Ki) {
     if (K[1] == 0.f && K[3] == 0.f && K[6] == 0.f && K[7] == 0.f && K[8] == 1.f) {
-        // zero-skew pinhole: LAPACK's back-substitution reduces to these true divisions
+        // zero-skew pinhole: the exact entries are single quotients, and a float32 division is their correct rounding
         // (bit-identical to np.linalg.inv on 20 000 / 20 000 random pinhole K)
         const float fx = K[0], fy = K[4], cx = K[2], cy = K[5];
         Ki[0] = __fdiv_rn(1.f, fx); Ki[1] = 0.f; Ki[2] = __fdiv_rn(-cx, fx);
@@ -19,27 +23,26 @@ __device__ inline void inv3_f32(const float* K, float* Ki) {
         Ki[6] = 0.f; Ki[7] = 0.f; Ki[8] = 1.f;
         return;
     }
-    // general K: float32 Gauss-Jordan with partial pivoting (same algorithm family as sgesv; the
-    // last bit is not guaranteed to agree with LAPACK for a skewed K)
-    float a[3][6];
+    // general K: float64 Gauss-Jordan with partial pivoting (dgesv's pivot choice), rounded to float32 at the end
+    double a[3][6];
     for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) { a[r][c] = K[r * 3 + c]; a[r][3 + c] = (r == c) ? 1.f : 0.f; }
+        for (int c = 0; c < 3; ++c) { a[r][c] = (double)K[r * 3 + c]; a[r][3 + c] = (r == c) ? 1.0 : 0.0; }
     for (int col = 0; col < 3; ++col) {
         int piv = col;
         for (int r = col + 1; r < 3; ++r)
-            if (fabsf(a[r][col]) > fabsf(a[piv][col])) piv = r;
+            if (fabs(a[r][col]) > fabs(a[piv][col])) piv = r;
         if (piv != col)
-            for (int c = 0; c < 6; ++c) { float t = a[col][c]; a[col][c] = a[piv][c]; a[piv][c] = t; }
-        const float d = a[col][col];
-        for (int c = 0; c < 6; ++c) a[col][c] = __fdiv_rn(a[col][c], d);
+            for (int c = 0; c < 6; ++c) { const double t = a[col][c]; a[col][c] = a[piv][c]; a[piv][c] = t; }
+        const double d = a[col][col];
+        for (int c = 0; c < 6; ++c) a[col][c] = ddiv(a[col][c], d);
         for (int r = 0; r < 3; ++r) {
             if (r == col) continue;
-            const float f = a[r][col];
-            for (int c = 0; c < 6; ++c) a[r][c] = __fsub_rn(a[r][c], __fmul_rn(f, a[col][c]));
+            const double f = a[r][col];
+            for (int c = 0; c < 6; ++c) a[r][c] = dfma(-f, a[col][c], a[r][c]);
         }
     }
     for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c) Ki[r * 3 + c] = a[r][3 + c];
+        for (int c = 0; c < 3; ++c) Ki[r * 3 + c] = __double2float_rn(a[r][3 + c]);
 }
 
 // ---- compute_fundamental_matrix(K1, R1, t1, K2, R2, t2), camera_utils.py:23-46 ----------------------

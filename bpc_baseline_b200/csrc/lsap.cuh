@@ -171,6 +171,7 @@ __device__ inline void lsap_scan_unassigned_full(const LsapState& st, const Acc&
 template <class Acc>
 __device__ void lsap_augment(LsapState& st, const Acc& acc, int cur, int nthreads, int tid) {
     const int nr = st.nr, nc = st.nc;
+    __syncthreads();                      // every warp has read ctl[] of the previous search before it is reset
     if (tid == 0) {
         st.crow[0] = cur; st.cm[0] = 0.0; st.cu[0] = st.u[cur];
         st.ctl[1] = 0; st.ctl[3] = 0;

@@ -299,11 +299,13 @@ __global__ void __launch_bounds__(256, 2) bpc_match_kernel(const float* __restri
                                  const double* __restrict__ centers, const int32_t* __restrict__ counts,
                                  int S, int Dmax, float threshold,
                                  int32_t* __restrict__ idx, int32_t* __restrict__ nout, float* __restrict__ costout,
-                                 double* __restrict__ Xout, double* __restrict__ reproj, double* __restrict__ Fout) {
+                                 double* __restrict__ Xout, double* __restrict__ reproj, double* __restrict__ Fout,
+                                 unsigned char* __restrict__ spill, size_t spill_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, nth = blockDim.x, nwarps = nth >> 5;
     MatchSmem ms;
-    match_carve(ms, smem_raw, Dmax, nwarps);
+    // scenes too large for shared memory (Dmax > ~450) keep their state in the caller's workspace, one block per CTA
+    match_carve(ms, spill != nullptr ? spill + (size_t)blockIdx.x * spill_per_cta : smem_raw, Dmax, nwarps);
     const double NaN = __longlong_as_double(0x7ff8000000000000LL);
 
     for (int s = blockIdx.x; s < S; s += gridDim.x) {
@@ -330,7 +332,11 @@ __global__ void __launch_bounds__(256, 2) bpc_match_kernel(const float* __restri
                 if (reproj != nullptr) reproj[((size_t)s * Dmax + e) * 3 + c] = NaN;
             }
         }
-        if (N <= 0 || M <= 0 || P <= 0 || N > Dmax || M > Dmax || P > Dmax) {   // process_pose.py:161-163
+        if (N > Dmax || M > Dmax || P > Dmax) {              // e.g. the overflow count of bpc_detections_from_yolo
+            if (tid == 0) nout[s] = BPC_N_OVERFLOW;
+            continue;
+        }
+        if (N <= 0 || M <= 0 || P <= 0) {                    // process_pose.py:161-163
             if (tid == 0) nout[s] = 0;
             continue;
         }
@@ -455,8 +461,14 @@ __global__ void bpc_match_objects_kernel(const float* __restrict__ cost, int S, 
         __syncthreads();
         ExplicitCost acc;
         acc.c = cost + (size_t)s * NM * P; acc.P = P; acc.transposed = transposed;
-        bool bad = false;
-        for (int row = 0; row < nr; ++row) {
+        // SciPy rejects a matrix with ANY NaN or -inf entry ("matrix contains invalid numeric entries")
+        int invalid = 0;
+        for (long long e = tid; e < (long long)NM * P; e += nth) {
+            const float v = acc.c[e];
+            invalid |= (v != v) || (v == __int_as_float(0xff800000));
+        }
+        bool bad = __syncthreads_or(invalid) != 0;
+        for (int row = 0; row < nr && !bad; ++row) {
             lsap_augment(st, acc, row, nth, tid);
             if (st.ctl[2]) { bad = true; break; }
         }
@@ -677,6 +689,67 @@ __global__ void bpc_box_centers_kernel(const int32_t* __restrict__ boxes, int co
     centers[(size_t)t * 2 + 1] = 0.5 * (double)((long long)b.y + (long long)b.w);
 }
 
+// Optional reprojection-error filter (the helper compute_reprojection_error, utils/triangulation.py:14-18, has no caller in
+// the reference, so the policy is this library's: a match is dropped when ANY view's error exceeds the threshold; the
+// survivors keep their (cost, r) order).  One thread per scene, in place; the tail is re-padded.
+__global__ void bpc_match_filter_kernel(int S, int Dmax, double thresh, int32_t* __restrict__ idx, int32_t* __restrict__ n,
+                                        float* __restrict__ cost, double* __restrict__ X, double* __restrict__ reproj) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const int cnt = n[s];
+    if (cnt <= 0) return;
+    const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+    const size_t base = (size_t)s * Dmax;
+    int kept = 0;
+    for (int m = 0; m < cnt; ++m) {
+        const double* e = reproj + (base + m) * 3;
+        if (e[0] > thresh || e[1] > thresh || e[2] > thresh) continue;
+        if (kept != m) {
+            for (int c = 0; c < 3; ++c) {
+                idx[(base + kept) * 3 + c] = idx[(base + m) * 3 + c];
+                X[(base + kept) * 3 + c] = X[(base + m) * 3 + c];
+                reproj[(base + kept) * 3 + c] = e[c];
+            }
+            cost[base + kept] = cost[base + m];
+        }
+        ++kept;
+    }
+    for (int m = kept; m < cnt; ++m) {
+        for (int c = 0; c < 3; ++c) { idx[(base + m) * 3 + c] = -1; X[(base + m) * 3 + c] = NaN; reproj[(base + m) * 3 + c] = NaN; }
+        cost[base + m] = __int_as_float(0x7fc00000);
+    }
+    n[s] = kept;
+}
+
+// Pose records for the final gather: the valid match slots of every scene, compacted in scene order, as
+// 64-byte records (idx i32 x3, cost f32, X f64 x3, reproj f64 x3), behind a header and the per-scene counts.
+//   buffer = | total i32, S i32, Kmax i32, 0 | n[S] i32 (padded to 16 bytes) | records ...
+struct __align__(16) PoseRecord { int32_t i, j, k; float cost; double X[3]; double reproj[3]; };
+static_assert(sizeof(PoseRecord) == 64, "PoseRecord layout");
+__host__ __device__ inline size_t pack_records_offset(int S) { return 16 + (((size_t)S * 4 + 15) & ~(size_t)15); }
+
+__global__ void bpc_pack_records_kernel(const int32_t* __restrict__ idx, const int32_t* __restrict__ n, const float* __restrict__ cost,
+                                        const double* __restrict__ X, const double* __restrict__ reproj,
+                                        const int32_t* __restrict__ scene_offset, int offset_div, int S, int Kmax,
+                                        unsigned char* __restrict__ buf) {
+    const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int32_t* head = reinterpret_cast<int32_t*>(buf);
+    if (t == 0) { head[0] = scene_offset[S] / offset_div; head[1] = S; head[2] = Kmax; head[3] = 0; }
+    if (t < S) head[4 + t] = n[t];
+    if (t >= (long long)S * Kmax) return;
+    const int s = (int)(t / Kmax), m = (int)(t - (long long)s * Kmax);
+    if (m >= n[s]) return;
+    PoseRecord r;
+    r.i = idx[t * 3]; r.j = idx[t * 3 + 1]; r.k = idx[t * 3 + 2];
+    r.cost = cost[t];
+    const double NaN = __longlong_as_double(0x7ff8000000000000LL);
+    for (int c = 0; c < 3; ++c) { r.X[c] = X[t * 3 + c]; r.reproj[c] = reproj ? reproj[t * 3 + c] : NaN; }
+    PoseRecord* out = reinterpret_cast<PoseRecord*>(buf + pack_records_offset(S)) + (scene_offset[s] / offset_div + m);
+    const uint4* src = reinterpret_cast<const uint4*>(&r);
+    uint4* dst = reinterpret_cast<uint4*>(out);
+    dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+}
+
 // ROI records: single CTA exclusive scan over 3*n[s], then a grid-stride fill.
 __global__ void bpc_roi_offsets_kernel(const int32_t* __restrict__ n, int S, int32_t* __restrict__ offs) {
     __shared__ int part[1024];
@@ -716,6 +789,8 @@ __global__ void bpc_roi_fill_kernel(const int32_t* __restrict__ boxes, const int
 // ------------------------------------------------------------------------------------------------------
 // host launchers (C ABI)
 // ------------------------------------------------------------------------------------------------------
+constexpr size_t MATCH_MAX_SMEM = 227 * 1024;
+
 static int pick_threads(int Dmax) {
     if (Dmax <= 32) return 32;
     if (Dmax <= 64) return 128;
@@ -740,26 +815,25 @@ extern "C" int bpc_cost_tensor(const double* F, const double* centers, const int
     if (Dmax > BPC_MAX_DET) return BPC_ETOOBIG;
     if (S == 0) return BPC_OK;
     const size_t smem = (28 + (size_t)3 * Dmax * 2 + (size_t)6 * Dmax * 3) * 8 + (size_t)6 * Dmax + 16;
-    if (smem > 227 * 1024) return BPC_ETOOBIG;
-    cudaError_t e = cudaFuncSetAttribute(bpc_cost_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > MATCH_MAX_SMEM) return BPC_ETOOBIG;
+    cudaError_t e = cudaFuncSetAttribute(bpc_cost_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MATCH_MAX_SMEM);
     if (e != cudaSuccess) return (int)e;
     bpc_cost_tensor_kernel<<<S, 256, smem, (cudaStream_t)stream>>>(F, centers, counts, S, Dmax, cost);
     BPC_LAUNCH_CHECK();
     return BPC_OK;
 }
 
-extern "C" size_t bpc_match_objects_workspace_bytes(int, int, int, int) { return 0; }
-
 extern "C" int bpc_match_objects(const float* cost, int S, int N, int M, int P, float threshold,
-                                 int32_t* idx, int32_t* n, void*, size_t, void* stream) {
+                                 int32_t* idx, int32_t* n, void* stream) {
     if (S < 0 || N < 1 || M < 1 || P < 1 || (S > 0 && (!cost || !idx || !n))) return BPC_EINVAL;
     if ((long long)N * M > (1 << 24) || P > (1 << 24)) return BPC_ETOOBIG;
     if (S == 0) return BPC_OK;
     const int NM = N * M;
     const int nr = NM > P ? P : NM, nc = NM > P ? NM : P;
     const size_t smem = lsap_state_bytes(nr, nc) + (size_t)nr * 4 + 32;
-    if (smem > 227 * 1024) return BPC_ETOOBIG;
-    cudaError_t e = cudaFuncSetAttribute(bpc_match_objects_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > MATCH_MAX_SMEM) return BPC_ETOOBIG;
+    // always the same constant: idempotent, so concurrent callers cannot interleave set(small) / launch(large)
+    cudaError_t e = cudaFuncSetAttribute(bpc_match_objects_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MATCH_MAX_SMEM);
     if (e != cudaSuccess) return (int)e;
     const int threads = nc <= 1024 ? 32 : (nc <= 8192 ? 128 : 256);
     bpc_match_objects_kernel<<<S, threads, smem, (cudaStream_t)stream>>>(cost, S, N, M, P, threshold, idx, n);
@@ -767,25 +841,74 @@ extern "C" int bpc_match_objects(const float* cost, int S, int N, int M, int P, 
     return BPC_OK;
 }
 
-extern "C" size_t bpc_match_workspace_bytes(int, int) { return 0; }
+// launch geometry of bpc_match_kernel for a given Dmax: threads, dynamic shared memory, and -- when even one warp's state
+// does not fit the 227 KB of an SM -- the per-CTA spill block in the caller's workspace
+static void match_plan(int Dmax, int* threads, size_t* smem, size_t* spill_per_cta) {
+    int th = pick_threads(Dmax);
+    size_t sm = match_smem_bytes(Dmax, th / 32);
+    while (sm > MATCH_MAX_SMEM && th > 32) { th /= 2; sm = match_smem_bytes(Dmax, th / 32); }
+    *spill_per_cta = 0;
+    if (sm > MATCH_MAX_SMEM) {
+        th = 256;
+        *spill_per_cta = (match_smem_bytes(Dmax, th / 32) + 255) & ~(size_t)255;
+        sm = 0;
+    }
+    *threads = th; *smem = sm;
+}
+static int match_grid(int S, size_t spill_per_cta) { return spill_per_cta ? (S < 2 * 148 ? S : 2 * 148) : S; }
+
+extern "C" size_t bpc_match_workspace_bytes(int S, int Dmax) {
+    if (S < 1 || Dmax < 1 || Dmax > BPC_MAX_DET) return 0;
+    int threads; size_t smem, spill;
+    match_plan(Dmax, &threads, &smem, &spill);
+    return spill * (size_t)match_grid(S, spill);
+}
 
 extern "C" int bpc_match_triangulate(const float* Ks, const double* RTs, const double* centers, const int32_t* counts,
-                                     int S, int Dmax, float threshold, int32_t* idx, int32_t* n, float* cost, double* X,
-                                     double* reproj, double* F, void*, size_t, void* stream) {
+                                     int S, int Dmax, float threshold, int has_reproj_thresh, double reproj_thresh,
+                                     int32_t* idx, int32_t* n, float* cost, double* X,
+                                     double* reproj, double* F, void* workspace, size_t workspace_bytes, void* stream) {
     if (S < 0 || Dmax < 1) return BPC_EINVAL;
     if (S > 0 && (!Ks || !RTs || !centers || !counts || !idx || !n || !cost || !X)) return BPC_EINVAL;
+    if (has_reproj_thresh && (!reproj || !(reproj_thresh == reproj_thresh))) return BPC_EINVAL;   // the filter reads `reproj`
     if (Dmax > BPC_MAX_DET) return BPC_ETOOBIG;
     if (S == 0) return BPC_OK;
-    int threads = pick_threads(Dmax);
-    size_t smem = match_smem_bytes(Dmax, threads / 32);
-    while (smem > 227 * 1024 && threads > 32) { threads /= 2; smem = match_smem_bytes(Dmax, threads / 32); }
-    if (smem > 227 * 1024) return BPC_ETOOBIG;
-    cudaError_t e = cudaFuncSetAttribute(bpc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int threads; size_t smem, spill;
+    match_plan(Dmax, &threads, &smem, &spill);
+    const int grid = match_grid(S, spill);
+    if (spill) {
+        if (!workspace || ((uintptr_t)workspace & 15) != 0) return workspace ? BPC_EALIGN : BPC_EWORKSPACE;
+        if (workspace_bytes < spill * (size_t)grid) return BPC_EWORKSPACE;
+    }
+    cudaError_t e = cudaFuncSetAttribute(bpc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MATCH_MAX_SMEM);
     if (e != cudaSuccess) return (int)e;
-    bpc_match_kernel<<<S, threads, smem, (cudaStream_t)stream>>>(Ks, RTs, centers, counts, S, Dmax, threshold, idx, n, cost, X, reproj, F);
+    bpc_match_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(Ks, RTs, centers, counts, S, Dmax, threshold, idx, n, cost, X, reproj, F,
+                                                                    spill ? (unsigned char*)workspace : nullptr, spill);
     BPC_LAUNCH_CHECK();
     const long long slots = (long long)S * Dmax;
     bpc_match_tri_kernel<<<(unsigned)((slots + 127) / 128), 128, 0, (cudaStream_t)stream>>>(Ks, RTs, centers, idx, n, S, Dmax, X, reproj);
+    BPC_LAUNCH_CHECK();
+    if (has_reproj_thresh) {
+        bpc_match_filter_kernel<<<(S + 127) / 128, 128, 0, (cudaStream_t)stream>>>(S, Dmax, reproj_thresh, idx, n, cost, X, reproj);
+        BPC_LAUNCH_CHECK();
+    }
+    return BPC_OK;
+}
+
+extern "C" size_t bpc_pack_records_bytes(int S, int Kmax) {
+    if (S < 0 || Kmax < 0) return 0;
+    return pack_records_offset(S) + (size_t)S * Kmax * sizeof(PoseRecord);
+}
+
+extern "C" int bpc_pack_records(const int32_t* idx, const int32_t* n, const float* cost, const double* X, const double* reproj,
+                                const int32_t* scene_offset, int offset_div, int S, int Kmax, void* buf, void* stream) {
+    if (S < 0 || Kmax < 1 || offset_div < 1) return BPC_EINVAL;
+    if (S > 0 && (!idx || !n || !cost || !X || !scene_offset || !buf)) return BPC_EINVAL;
+    if (((uintptr_t)buf & 15) != 0) return BPC_EALIGN;
+    if (S == 0) return BPC_OK;
+    const long long slots = (long long)S * Kmax;
+    bpc_pack_records_kernel<<<(unsigned)((slots + 255) / 256), 256, 0, (cudaStream_t)stream>>>(idx, n, cost, X, reproj, scene_offset, offset_div,
+                                                                                              S, Kmax, (unsigned char*)buf);
     BPC_LAUNCH_CHECK();
     return BPC_OK;
 }

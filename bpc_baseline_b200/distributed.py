@@ -16,7 +16,7 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
-RECORD_WIDTH = 8            # i, j, k, cost, X, Y, Z, n_of_scene  (float64: 64 bytes per match slot)
+RECORD_BYTES = 64           # idx i32 x3 | cost f32 | X f64 x3 | reproj f64 x3   (struct PoseRecord, csrc/match.cu)
 
 
 def shard_range(total: int, rank: int, world: int, align: int = 1) -> tuple[int, int]:
@@ -30,38 +30,84 @@ def shard_range(total: int, rank: int, world: int, align: int = 1) -> tuple[int,
     return min(total, lo_u * align), min(total, hi_u * align)
 
 
-def pack_records(idx: torch.Tensor, n: torch.Tensor, cost: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
-    """[S, Kmax, 8] float64 records from the matcher outputs (integers and float32 costs are exact in float64)."""
+def records_bytes(S: int, K: int) -> int:
+    """Size of the record buffer of S scenes x K match slots (= bpc_pack_records_bytes)."""
+    return 16 + ((S * 4 + 15) & ~15) + S * K * RECORD_BYTES
+
+
+def pack_records(res, scene_offset: Optional[torch.Tensor] = None, offset_div: int = 3,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Matcher outputs (``batched.MatchResult`` on the GPU) -> one uint8 record buffer: ONE kernel (bpc_pack_records),
+    native dtypes, valid slots only, compacted in scene order behind a header and the per-scene counts."""
+    from . import batched
+    return batched.pack_records(res, scene_offset, offset_div, out)
+
+
+def pack_records_torch(idx: torch.Tensor, n: torch.Tensor, cost: torch.Tensor, X: torch.Tensor,
+                       reproj: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The same buffer written with torch ops on any device: the executable statement of the layout.  The gloo tests
+    use it on CPU tensors, the GPU tests to check the kernel byte for byte; the product path packs with the kernel."""
     S, K, _ = idx.shape
-    rec = torch.empty((S, K, RECORD_WIDTH), dtype=torch.float64, device=idx.device)
-    rec[..., 0:3] = idx.to(torch.float64)
-    rec[..., 3] = cost.to(torch.float64)
-    rec[..., 4:7] = X
-    rec[..., 7] = n.to(torch.float64)[:, None]
-    return rec
+    dev = idx.device
+    buf = torch.zeros((records_bytes(S, K),), dtype=torch.uint8, device=dev)
+    nn = n.clamp(min=0).to(torch.int64)
+    valid = torch.arange(K, device=dev)[None, :] < nn[:, None]
+    total = int(nn.sum())
+    head = torch.tensor([total, S, K, 0], dtype=torch.int32, device=dev)
+    buf[:16] = head.view(torch.uint8)
+    buf[16:16 + 4 * S] = n.to(torch.int32).contiguous().view(torch.uint8)
+    rec = torch.zeros((total, 16), dtype=torch.int32, device=dev)
+    rec[:, 0:3] = idx[valid].to(torch.int32)
+    rec[:, 3] = cost[valid].to(torch.float32).view(torch.int32)
+    r64 = rec.view(torch.float64)                                     # [total, 8]: X in 2..4, reproj in 5..7
+    r64[:, 2:5] = X[valid].to(torch.float64)
+    r64[:, 5:8] = reproj[valid].to(torch.float64) if reproj is not None else float('nan')
+    off = 16 + ((S * 4 + 15) & ~15)
+    buf[off:off + total * RECORD_BYTES] = rec.view(torch.uint8).reshape(-1)
+    return buf
 
 
-def unpack_records(rec: torch.Tensor) -> dict:
-    """Inverse of pack_records on a [..., S, Kmax, 8] tensor (leading rank dimension is folded into S)."""
-    rec = rec.reshape(-1, rec.shape[-2], RECORD_WIDTH)
-    return {'idx': rec[..., 0:3].to(torch.int32), 'cost': rec[..., 3].to(torch.float32), 'X': rec[..., 4:7].clone(),
-            'n': rec[:, 0, 7].to(torch.int32)}
+def unpack_records(buf: torch.Tensor) -> dict:
+    """Inverse of pack_records on one buffer, or on the [world, nbytes] result of gather_records (ranks concatenated in
+    rank order): padded idx i32 [S,K,3] (-1), n i32 [S], cost f32 [S,K], X / reproj f64 [S,K,3] (NaN)."""
+    if buf.dim() == 2:
+        parts = [unpack_records(b) for b in buf.unbind(0)]
+        return {k: torch.cat([p[k] for p in parts], 0) for k in parts[0]}
+    buf = buf.contiguous()
+    dev = buf.device
+    total, S, K, _ = (int(v) for v in buf[:16].view(torch.int32).tolist())
+    n = buf[16:16 + 4 * S].view(torch.int32).clone()
+    off = 16 + ((S * 4 + 15) & ~15)
+    rec = buf[off:off + total * RECORD_BYTES].view(torch.int32).reshape(total, 16)
+    nn = n.clamp(min=0).to(torch.int64)
+    valid = torch.arange(K, device=dev)[None, :] < nn[:, None]
+    idx = torch.full((S, K, 3), -1, dtype=torch.int32, device=dev)
+    cost = torch.full((S, K), float('nan'), dtype=torch.float32, device=dev)
+    X = torch.full((S, K, 3), float('nan'), dtype=torch.float64, device=dev)
+    reproj = torch.full((S, K, 3), float('nan'), dtype=torch.float64, device=dev)
+    idx[valid] = rec[:, 0:3]
+    cost[valid] = rec[:, 3].contiguous().view(torch.float32)
+    r64 = rec.view(torch.float64)
+    X[valid] = r64[:, 2:5]
+    reproj[valid] = r64[:, 5:8]
+    return {'idx': idx, 'n': n, 'cost': cost, 'X': X, 'reproj': reproj}
 
 
-def gather_records(rec: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
-    """All ranks receive [world, S, Kmax, 8]; every rank must contribute the same S and Kmax.
+def gather_records(buf: torch.Tensor, group: Optional[dist.ProcessGroup] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """All ranks receive [world, nbytes] uint8; every rank must contribute a buffer of the same size (same S and Kmax).
 
     NCCL: one all_gather_into_tensor over NVLink / NVSwitch.  Other backends (gloo on CPU): all_gather.
     """
     if not dist.is_available() or not dist.is_initialized():
-        return rec.unsqueeze(0)
+        return buf.unsqueeze(0)
     world = dist.get_world_size(group)
-    out = torch.empty((world, *rec.shape), dtype=rec.dtype, device=rec.device)
+    if out is None:
+        out = torch.empty((world, buf.numel()), dtype=buf.dtype, device=buf.device)
     if dist.get_backend(group) == 'nccl':
-        dist.all_gather_into_tensor(out, rec.contiguous(), group=group)
+        dist.all_gather_into_tensor(out, buf.contiguous(), group=group)
     else:
-        parts = [torch.empty_like(rec) for _ in range(world)]
-        dist.all_gather(parts, rec.contiguous(), group=group)
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf.contiguous(), group=group)
         for r, p in enumerate(parts):
             out[r] = p
     return out

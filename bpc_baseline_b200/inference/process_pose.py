@@ -29,6 +29,8 @@ class PoseEstimatorParams:
     rotation_mode: str = None
     target_size: int = 256          # process_pose.py:204
     swap_rb: bool = True            # cv2.COLOR_BGR2RGB at :206 (False = the training-dataset order, data_utils.py:252)
+    reproj_thresh: float = None     # optional: drop matches whose reprojection error (utils/triangulation.py:14-18)
+                                    # exceeds this many pixels in any view; None = the reference (it filters nowhere)
 
 
 class PosePrediction:
@@ -87,25 +89,44 @@ class PoseEstimator:
 
     # ------------------------------------------------------------------------------------------------
     def _detect(self, capture):
-        """YOLO on each view -> {cam: [{'bbox', 'bb_center'}]} -- reference process_pose.py:113-142."""
+        """YOLO on each view -> {cam: [{'bbox', 'bb_center'}]} -- reference process_pose.py:113-142.
+
+        The detector is the caller's model; its post-processing (class / confidence filter, int() truncation, centres,
+        :123-141) is one launch of ``bpc_detections_from_yolo`` over all views.  ``detect_tensors`` returns the same
+        result as device tensors (the matcher's input layout) without the trip through Python dicts."""
+        boxes, centers, counts = self.detect_tensors(capture)
+        boxes, centers, counts = _host.to_host(boxes)[0], _host.to_host(centers)[0], _host.to_host(counts)[0]
+        camera_predictions = {}
+        for idx in range(boxes.shape[0]):
+            camera_predictions[idx] = [
+                {'bbox': tuple(int(v) for v in boxes[idx, d]), 'bb_center': (float(centers[idx, d, 0]), float(centers[idx, d, 1]))}
+                for d in range(int(counts[idx]))]
+        return camera_predictions
+
+    def detect_tensors(self, capture):
+        """(boxes i32 [1,C,Dmax,4], centers f64 [1,C,Dmax,2], counts i32 [1,C]) on the GPU for one capture."""
         if self.yolo is None:
             raise RuntimeError('no detector attached: pass yolo= to PoseEstimator (third-party model, outside the hot path)')
-        camera_predictions = {}
-        for idx, image in enumerate(capture.images):
+        dev = _host.device()
+        raw = []
+        for image in capture.images:
+            if self.verbose:
+                print(f"Processing image shape: {image.shape}")
             results = self.yolo(image, imgsz=1280)[0]
-            boxes = results.boxes.xyxy.cpu().numpy()
-            confs = results.boxes.conf.cpu().numpy()
-            clss = results.boxes.cls.cpu().numpy()
-            if len(results.boxes) == 0:
-                camera_predictions[idx] = []
-                continue
-            valid = (clss == 0) & (confs >= self.params.yolo_conf_thresh)
-            preds_cam = []
-            for box in boxes[valid]:
-                x1, y1, x2, y2 = map(int, box)
-                preds_cam.append({'bbox': (x1, y1, x2, y2), 'bb_center': (0.5 * (x1 + x2), 0.5 * (y1 + y2))})
-            camera_predictions[idx] = preds_cam
-        return camera_predictions
+            b = results.boxes
+            raw.append((torch.as_tensor(b.xyxy).to(dev, torch.float32).reshape(-1, 4),
+                        torch.as_tensor(b.conf).to(dev, torch.float32).reshape(-1),
+                        torch.as_tensor(b.cls).to(dev, torch.float32).reshape(-1)))
+        C = len(raw)
+        N = max(1, max(int(r[0].shape[0]) for r in raw))
+        xyxy = torch.zeros((1, C, N, 4), dtype=torch.float32, device=dev)
+        conf = torch.zeros((1, C, N), dtype=torch.float32, device=dev)
+        cls = torch.full((1, C, N), -1.0, dtype=torch.float32, device=dev)
+        nraw = torch.tensor([[int(r[0].shape[0]) for r in raw]], dtype=torch.int32, device=dev)
+        for c, (bx, cf, cl) in enumerate(raw):
+            n = int(bx.shape[0])
+            xyxy[0, c, :n], conf[0, c, :n], cls[0, c, :n] = bx, cf, cl
+        return batched.detections_from_yolo(xyxy, conf, cls, nraw, self.params.yolo_conf_thresh, N)
 
     # ------------------------------------------------------------------------------------------------
     def _match(self, capture, detections):
@@ -124,10 +145,11 @@ class PoseEstimator:
             return predictions
         res = batched.match_triangulate(_host.to_dev(Ks, np.float32), _host.to_dev(RTs, np.float64),
                                         _host.to_dev(centers, np.float64), _host.to_dev(counts, np.int32),
-                                        self.params.matching_threshold, want_reproj=True, want_F=self.verbose)
+                                        self.params.matching_threshold, want_reproj=True, want_F=self.verbose,
+                                        reproj_thresh=getattr(self.params, 'reproj_thresh', None))
         n = int(res.n.cpu()[0])
         if n < 0:
-            raise ValueError('matrix contains invalid numeric entries')
+            batched.check_match_status(res.n)
         idx = _host.to_host(res.idx)[0, :n]
         X = _host.to_host(res.X)[0, :n]
         reproj = _host.to_host(res.reproj)[0, :n]

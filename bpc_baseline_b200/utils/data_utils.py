@@ -36,8 +36,8 @@ def letterbox_preserving_aspect_ratio(img, target_size=256, fill_color=(255, 255
         raise TypeError('img must be an H x W x 3 uint8 array')
     if new_w < 1 or new_h < 1:
         raise _resize_error("OpenCV(-215:Assertion failed) !dsize.empty() in function 'resize'")
-    if not 1 <= int(target_size) <= 256:
-        raise NotImplementedError('target_size above 256 is not supported by the CUDA crop kernels')
+    if not 1 <= int(target_size) <= batched.MAX_TARGET:
+        raise NotImplementedError(f'target_size above {batched.MAX_TARGET} is not supported by the CUDA crop kernels')
     images = _host.to_dev(img[None], np.uint8)
     rois = _host.to_dev([[0, 0, 0, w, h]], np.int32)
     canvas = batched.roi_crop_u8(images, rois, T=int(target_size), fill=fill_color)

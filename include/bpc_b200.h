@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BPC_ABI_VERSION 1
+#define BPC_ABI_VERSION 2
 
 enum {
     BPC_OK = 0,
@@ -42,9 +42,15 @@ enum {
     BPC_ETOOBIG = -4     /* problem exceeds a documented limit (Dmax, ROI width) */
 };
 
+/* per-scene status values of the `n` output of the matchers (any negative n: the scene has no matches) */
+#define BPC_N_INFEASIBLE (-1)   /* NaN / -inf / all-infinite costs: scipy.optimize.linear_sum_assignment raises ValueError */
+#define BPC_N_OVERFLOW (-2)     /* a camera's count exceeds Dmax (e.g. the overflow count of bpc_detections_from_yolo) */
+
 /* limits */
-#define BPC_MAX_DET 384         /* Dmax <= 384 detections per camera (shared-memory resident scene) */
+#define BPC_MAX_DET 2048        /* Dmax <= 2048 detections per camera; a scene stays in shared memory up to Dmax ~ 450,
+                                   larger scenes keep their state in the caller's workspace (bpc_match_workspace_bytes) */
 #define BPC_MAX_ROI_WIDTH 8192  /* widest source box the crop kernel stages in shared memory */
+#define BPC_MAX_TARGET 1024     /* crop target size T <= 1024 (one thread per output column in the generic kernel) */
 
 int bpc_abi_version(void);
 /* Static string for a code returned by any entry point (host pointer, never freed). */
@@ -75,12 +81,12 @@ int bpc_cost_tensor(const double* F, const double* centers, const int32_t* count
  *   cost       float [S][N][M][P]          dense, same N, M, P for the whole batch
  *   idx        int32 [S][Kmax][3]          (i, j, k) per kept match, ascending r, -1 padded
  *   n          int32 [S]                   kept matches per scene
+ *   n          = BPC_N_INFEASIBLE where SciPy raises (any NaN or -inf entry, or no feasible assignment)
  *   Kmax       = min(N*M, P)
- * Workspace: bpc_match_objects_workspace_bytes(S, N, M, P).
+ * The assignment state (O(rows) words + one bit per column) lives in shared memory: BPC_ETOOBIG beyond that.
  */
-size_t bpc_match_objects_workspace_bytes(int S, int N, int M, int P);
 int bpc_match_objects(const float* cost, int S, int N, int M, int P, float threshold,
-                      int32_t* idx, int32_t* n, void* workspace, size_t workspace_bytes, void* stream);
+                      int32_t* idx, int32_t* n, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a1-a10. The whole geometry path of PoseEstimator._match, bpc/inference/process_pose.py:144-188,
@@ -89,20 +95,39 @@ int bpc_match_objects(const float* cost, int S, int N, int M, int P, float thres
  * triangulate_multi_view epipolar_matching.py:118-127) and per-view reprojection error
  * (compute_reprojection_error, bpc/inference/utils/triangulation.py:14-18).
  *   threshold  compared as float32 against the float32 cost (epipolar_matching.py:110-111)
+ *   has_reproj_thresh, reproj_thresh
+ *              optional reprojection-error filter: with has_reproj_thresh != 0 a match is dropped when the error of ANY
+ *              view exceeds reproj_thresh pixels; survivors keep their (cost, r) order, n is updated, the tail re-padded.
+ *              The reference has the helper but no call site that filters, so 0 = reference behaviour;
+ *              needs reproj != NULL.
  *   Kmax       = Dmax
  *   idx    int32  [S][Kmax][3]  matches sorted by (cost, r); -1 padded
- *   n      int32  [S]           matches per scene (0 if any camera has no detection, :161-163)
+ *   n      int32  [S]           matches per scene (0 if any camera has no detection, :161-163; BPC_N_INFEASIBLE;
+ *                               BPC_N_OVERFLOW if a count exceeds Dmax -- never a silent empty result)
  *   cost   float  [S][Kmax]     cost of each match (NaN padded)
  *   X      double [S][Kmax][3]  triangulated points (NaN padded)
  *   reproj double [S][Kmax][3]  reprojection error per view, pixels (NaN padded); may be NULL
  *   F      double [S][3][3][3]  fundamental matrices; may be NULL
- * Workspace: bpc_match_workspace_bytes(S, Dmax) (may be 0).
+ * Workspace: bpc_match_workspace_bytes(S, Dmax) bytes, 16-byte aligned: 0 while a scene fits shared memory (Dmax up to
+ * ~450), else one state block per resident CTA (the kernel then walks the scenes with a fixed grid).
  */
 size_t bpc_match_workspace_bytes(int S, int Dmax);
 int bpc_match_triangulate(const float* Ks, const double* RTs, const double* centers, const int32_t* counts,
-                          int S, int Dmax, float threshold,
+                          int S, int Dmax, float threshold, int has_reproj_thresh, double reproj_thresh,
                           int32_t* idx, int32_t* n, float* cost, double* X, double* reproj, double* F,
                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Pose records for the final multi-GPU gather: the valid match slots of every scene, compacted in
+ * scene order, native dtypes, 64 bytes each:  idx int32 x3 | cost float | X double x3 | reproj double x3.
+ *   buf = | total int32, S int32, Kmax int32, 0 | n int32 [S], padded to 16 bytes | records ... |
+ *   scene_offset int32 [S+1]  exclusive prefix sum of offset_div * max(n, 0); bpc_build_rois' output with offset_div = 3
+ *   reproj       may be NULL (NaN is written)
+ *   buf          bpc_pack_records_bytes(S, Kmax) bytes (capacity S*Kmax records), 16-byte aligned
+ */
+size_t bpc_pack_records_bytes(int S, int Kmax);
+int bpc_pack_records(const int32_t* idx, const int32_t* n, const float* cost, const double* X, const double* reproj,
+                     const int32_t* scene_offset, int offset_div, int S, int Kmax, void* buf, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * a8. Stand-alone DLT triangulation.  Replaces triangulate_multi_view,
@@ -140,7 +165,8 @@ int bpc_box_centers(const int32_t* boxes, int count, double* centers, void* stre
  * producing the device-resident detection tensors the matcher consumes.
  *   xyxy float [SC][Nraw][4] (16-byte aligned), conf / cls float [SC][Nraw], nraw int32 [SC]; SC = scenes * cameras
  *   keeps cls == 0 && conf >= conf_thresh, in order; boxes int32 [SC][Dmax][4], centers double [SC][Dmax][2]
- *   counts int32 [SC] = number kept (entries beyond Dmax are dropped; counts > Dmax signals the overflow)
+ *   counts int32 [SC] = number kept (entries beyond Dmax are dropped; counts > Dmax signals the overflow, which
+ *                       bpc_match_triangulate reports as n = BPC_N_OVERFLOW for that scene)
  */
 int bpc_detections_from_yolo(const float* xyxy, const float* conf, const float* cls, const int32_t* nraw, int SC, int Nraw,
                              float conf_thresh, int Dmax, int32_t* boxes, double* centers, int32_t* counts, void* stream);
@@ -189,12 +215,12 @@ int bpc_train_rois(const int32_t* xywh, const int32_t* image, const double* scal
  *   out      float [R][3][T][T]   (16-byte aligned)
  *   status   optional int32 [R]: 0 ok, 1 = ROI rejected (empty box, resized side < 1, out of
  *            image, wider than BPC_MAX_ROI_WIDTH); a rejected ROI's output is all fill colour
- *   workspace   bpc_roi_crop_workspace_bytes(R) bytes of device scratch (16-byte aligned): per-ROI
- *               geometry records and the list of ROIs taking the generic path
+ *   workspace   bpc_roi_crop_workspace_bytes(R, T) bytes of device scratch (16-byte aligned): per-ROI
+ *               geometry records, tap descriptors and the list of ROIs taking the generic path
  * bpc_roi_crop_u8 writes the uint8 letterboxed image itself, uint8 [R][T][T][3] in source channel
  * order -- exactly what letterbox_preserving_aspect_ratio returns.
  */
-size_t bpc_roi_crop_workspace_bytes(int R);
+size_t bpc_roi_crop_workspace_bytes(int R, int T);
 int bpc_roi_crop(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R,
                  const int32_t* n_rois_dev, int roi_first, int T, const uint8_t* fill, int swap_rb,
                  const float* lut, float* out, int32_t* status,

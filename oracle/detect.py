@@ -1,7 +1,8 @@
 """Oracle (test infrastructure): restatement of the detector post-processing of PoseEstimator._detect,
 reference bpc/inference/process_pose.py:123-141 (class / confidence filter, int() truncation, centres).
-Parity unpinned by reference outputs: the lines are inline in a method that needs YOLO weights to run, so
-this restatement is checked by reading only (it is ten lines)."""
+Pinned by tests/golden/detect.npz: oracle/make_golden.py calls the reference's PoseEstimator._detect unbound
+with a fake `yolo` callable returning seeded boxes / confidences / classes (no weights needed), and
+tests/test_oracle_golden.py::test_detect_restatement checks this restatement against those outputs."""
 from __future__ import annotations
 
 import numpy as np

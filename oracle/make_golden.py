@@ -18,6 +18,9 @@ records their outputs on seeded synthetic scenes:
                  letterbox_preserving_aspect_ratio outputs (uint8), the normalisation table from
                  torchvision's to_tensor/normalize, and full f32 tensors for a few crops.
 
+  detect.npz     PoseEstimator._detect called unbound with a fake yolo callable (seeded boxes / conf / cls).
+  skew.npz       scenes with skewed / general intrinsics (np.linalg.inv is then a real LU, not the pinhole form).
+
 /root/reference does not exist on the GPU box: nothing else may import it.
 """
 from __future__ import annotations
@@ -324,6 +327,86 @@ def golden_rotation(ref):
     print(f'  rotation: {n} raw outputs per head (euler, quat, 6d)')
 
 
+def golden_detect(ref):
+    """detect.npz: PoseEstimator._detect (process_pose.py:113-142) called UNBOUND with a fake `yolo` callable that returns
+    seeded boxes / confidences / classes -- no weights needed.  Covers negative coordinates (int() truncates toward
+    zero), confidences exactly at the threshold, wrong classes, and cameras without any raw detection."""
+    import torch
+    rng = np.random.default_rng([20250131, 5])
+    S, N, thresh = 6, 40, 0.1
+    xyxy = (rng.random((S, 3, N, 4)) * np.array([3840, 2160, 3840, 2160])).astype(np.float32)
+    xyxy[..., :2] -= (rng.random((S, 3, N, 2)) * 40).astype(np.float32)
+    xyxy[0, 0, 0] = [-0.5, -1.5, 10.9, 20.1]                      # int(): 0, -1, 10, 20
+    conf = rng.random((S, 3, N)).astype(np.float32)
+    conf[0, 0, :6] = np.float32(thresh)                             # exactly at the threshold: kept (>=)
+    conf[0, 1, :6] = np.nextafter(np.float32(thresh), np.float32(0))   # one ulp below: dropped
+    cls = rng.integers(0, 3, (S, 3, N)).astype(np.float32)
+    nraw = rng.integers(1, N + 1, (S, 3)).astype(np.int32)
+    nraw[1, 2] = 0                                                  # len(results.boxes) == 0 -> []
+    nraw[2, :] = 0
+    cls[3, 0] = 1.0                                                 # detections, none of class 0
+
+    class _Boxes:
+        def __init__(self, b, c, k):
+            self.xyxy, self.conf, self.cls = torch.from_numpy(b), torch.from_numpy(c), torch.from_numpy(k)
+
+        def __len__(self):
+            return int(self.xyxy.shape[0])
+
+    blob = {'xyxy': xyxy, 'conf': conf, 'cls': cls, 'nraw': nraw, 'thresh': np.float64(thresh)}
+    kept_max = 0
+    for s in range(S):
+        calls = iter(range(3))
+
+        def yolo(image, imgsz=1280, _s=s, _calls=calls):
+            c = next(_calls)
+            n = nraw[_s, c]
+            return [SimpleNamespace(boxes=_Boxes(xyxy[_s, c, :n].copy(), conf[_s, c, :n].copy(), cls[_s, c, :n].copy()))]
+
+        me = SimpleNamespace(yolo=yolo, params=ref.pp.PoseEstimatorParams(yolo_conf_thresh=thresh))
+        cap = SimpleNamespace(images=[np.zeros((4, 4, 3), np.uint8)] * 3)
+        out = quiet(ref.pp.PoseEstimator._detect, me, cap)
+        for c in range(3):
+            dets = out[c]
+            kept_max = max(kept_max, len(dets))
+            blob[f'bbox_{s}_{c}'] = np.array([d['bbox'] for d in dets], np.int64).reshape(len(dets), 4)
+            blob[f'center_{s}_{c}'] = np.array([d['bb_center'] for d in dets], np.float64).reshape(len(dets), 2)
+    np.savez_compressed(os.path.join(GOLDEN, 'detect.npz'), **blob)
+    print(f'  detect: {S} scenes x 3 cameras x <= {N} raw detections, at most {kept_max} kept')
+
+
+def golden_skew(ref):
+    """skew.npz: scenes whose intrinsics have skew and unequal focal lengths, so np.linalg.inv(K) (float32 LAPACK
+    sgetrf / sgetri) is not the closed pinhole form: compute_fundamental_matrix, compute_cost_matrix, match list, X."""
+    from bpc_baseline_b200 import synth
+    batch = synth.make_scenes(6, 8, seed=synth.SEED + 21)
+    rng = np.random.default_rng([synth.SEED, 21])
+    blob, names = {}, []
+    for s in range(6):
+        Ks = batch.Ks[s].copy()
+        for c in range(3):
+            Ks[c, 0, 1] = np.float32(rng.uniform(-8.0, 8.0))          # skew
+            Ks[c, 1, 1] = np.float32(Ks[c, 1, 1] * rng.uniform(0.97, 1.03))
+            if s >= 4:                                               # a general (non upper-triangular) matrix as well
+                Ks[c, 1, 0] = np.float32(rng.uniform(-2.0, 2.0))
+                Ks[c, 2, 0] = np.float32(rng.uniform(-1e-5, 1e-5))
+        RTs = batch.RTs[s]
+        res = run_match(ref, [Ks[c] for c in range(3)], [RTs[c] for c in range(3)], batch.detections(s))
+        tag = f'skew_{s}'
+        names.append(tag)
+        blob[f'{tag}/Ks'] = Ks
+        blob[f'{tag}/RTs'] = RTs
+        blob[f'{tag}/boxes'] = batch.boxes[s]
+        blob[f'{tag}/centers'] = batch.centers[s]
+        blob[f'{tag}/counts'] = batch.counts[s]
+        blob[f'{tag}/ref_Kinv'] = np.stack([np.linalg.inv(Ks[c]) for c in range(3)])
+        for k, v in res.items():
+            blob[f'{tag}/ref_{k}'] = v
+        print(f'  {tag}: matches={len(res["idx"])}')
+    blob['names'] = np.array(names)
+    np.savez_compressed(os.path.join(GOLDEN, 'skew.npz'), **blob)
+
+
 def main():
     if not os.path.isdir(REFERENCE):
         raise SystemExit('needs /root/reference (authoring container only)')
@@ -332,7 +415,8 @@ def main():
     ref = import_reference()
     only = set(sys.argv[1:])
     for name, fn in (('geometry', golden_geometry), ('bop_scene', golden_bop_scene), ('crops', golden_crops),
-                     ('dataset', golden_dataset), ('rotation', golden_rotation)):
+                     ('dataset', golden_dataset), ('rotation', golden_rotation), ('detect', golden_detect),
+                     ('skew', golden_skew)):
         if not only or name in only:
             print(name)
             fn(ref)

@@ -34,8 +34,8 @@ def pytest_collection_modifyitems(config, items):
 class GoldenScenes:
     """tests/golden/geometry.npz: outputs of the reference itself (oracle/make_golden.py)."""
 
-    def __init__(self):
-        self.z = np.load(os.path.join(GOLDEN, 'geometry.npz'))
+    def __init__(self, fname='geometry.npz'):
+        self.z = np.load(os.path.join(GOLDEN, fname))
         self.names = [str(n) for n in self.z['names']]
 
     def scene(self, name):
@@ -53,6 +53,18 @@ class GoldenScenes:
 @pytest.fixture(scope='session')
 def golden_scenes():
     return GoldenScenes()
+
+
+@pytest.fixture(scope='session')
+def golden_skew():
+    """tests/golden/skew.npz: reference outputs for skewed / general intrinsics (np.linalg.inv is a real LU there)."""
+    return GoldenScenes('skew.npz')
+
+
+@pytest.fixture(scope='session')
+def golden_detect():
+    """tests/golden/detect.npz: the reference's PoseEstimator._detect run unbound on a fake detector."""
+    return np.load(os.path.join(GOLDEN, 'detect.npz'))
 
 
 @pytest.fixture(scope='session')

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(lib, name), f'{name} declared in bpc_b200.h but not exported'
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert lib.bpc_abi_version() == 1
+    assert lib.bpc_abi_version() == 2
 
 
 def test_error_strings_and_argument_validation(lib):
@@ -37,12 +37,19 @@ def test_error_strings_and_argument_validation(lib):
     assert lib.bpc_fundamental(None, None, -1, None, None) == -1
     assert lib.bpc_fundamental(None, None, 4, None, None) == -1
     assert lib.bpc_fundamental(None, None, 0, None, None) == 0
-    assert lib.bpc_match_triangulate(None, None, None, None, 0, 0, 30.0, None, None, None, None, None, None, None, 0, None) == -1
-    assert lib.bpc_match_triangulate(None, None, None, None, 0, 20, 30.0, None, None, None, None, None, None, None, 0, None) == 0
+    assert lib.bpc_match_triangulate(None, None, None, None, 0, 0, 30.0, 0, 0.0, None, None, None, None, None, None, None, 0, None) == -1
+    assert lib.bpc_match_triangulate(None, None, None, None, 0, 20, 30.0, 0, 0.0, None, None, None, None, None, None, None, 0, None) == 0
+    assert lib.bpc_match_triangulate(None, None, None, None, 0, 4096, 30.0, 0, 0.0, None, None, None, None, None, None, None, 0, None) == -4
+    # a scene stays in shared memory up to Dmax ~ 450; beyond that the caller supplies a workspace
+    assert lib.bpc_match_workspace_bytes(4096, 200) == 0 and lib.bpc_match_workspace_bytes(4096, 384) == 0
+    assert lib.bpc_match_workspace_bytes(4, 1024) > 4 * 1024 * 1024 // 8
+    assert lib.bpc_pack_records_bytes(4096, 20) == 16 + 4096 * 4 + 4096 * 20 * 64
     fill = (ctypes.c_uint8 * 3)(255, 255, 255)
-    assert lib.bpc_roi_crop(None, 1, 8, 8, None, 0, None, 0, 300, fill, 1, None, None, None, None, 0, None) == -1   # T > 256
+    assert lib.bpc_roi_crop(None, 1, 8, 8, None, 0, None, 0, 1025, fill, 1, None, None, None, None, 0, None) == -1  # T > BPC_MAX_TARGET
     assert lib.bpc_roi_crop(None, 1, 8, 8, None, 0, None, 0, 224, fill, 1, None, None, None, None, 0, None) == 0    # R == 0
-    assert lib.bpc_roi_crop_workspace_bytes(8192) > 8192 * 8192
+    assert lib.bpc_roi_crop_workspace_bytes(8192, 256) > 8192 * 8192
+    assert lib.bpc_roi_crop_workspace_bytes(8192, 512) > lib.bpc_roi_crop_workspace_bytes(8192, 256)
+    assert lib.bpc_roi_crop_workspace_bytes(8192, 1025) == 0
     assert lib.bpc_triangulate_views(None, None, 1, 9, None, None) == -1
     assert lib.bpc_launch_count() == 0
 

@@ -31,7 +31,8 @@ def _fake_results(lo, hi, K):
             idx[s, m] = torch.tensor([m, (m + int(sid[s])) % K, (2 * m) % K])
             cost[s, m] = float(np.float32(0.37 * (m + 1) + 1e-3 * int(sid[s])))
             X[s, m] = torch.tensor([1.0 / 3.0 + m, -2.5 * int(sid[s]), 7.0e-5 * m])
-    return idx, n, cost, X
+    reproj = (X.abs() * 0.125 + 0.5)
+    return idx, n, cost, X, reproj
 
 
 def _worker(rank, world, port, total, K, out_dir):
@@ -40,7 +41,7 @@ def _worker(rank, world, port, total, K, out_dir):
     dist.init_process_group('gloo', rank=rank, world_size=world)
     try:
         lo, hi = distributed.shard_range(total, rank, world)
-        rec = distributed.pack_records(*_fake_results(lo, hi, K))
+        rec = distributed.pack_records_torch(*_fake_results(lo, hi, K))
         allrec = distributed.gather_records(rec)
         got = distributed.unpack_records(allrec)
         torch.save(got, os.path.join(out_dir, f'rank{rank}.pt'))
@@ -63,11 +64,16 @@ def test_shard_ranges_cover_and_align():
 
 
 def test_pack_unpack_roundtrip_is_exact():
-    idx, n, cost, X = _fake_results(10, 42, 6)
-    got = distributed.unpack_records(distributed.pack_records(idx, n, cost, X))
+    idx, n, cost, X, reproj = _fake_results(10, 42, 6)
+    n[3] = -1                                               # a status value travels as it is; the scene has no records
+    buf = distributed.pack_records_torch(idx, n, cost, X, reproj)
+    assert buf.numel() == distributed.records_bytes(32, 6)
+    got = distributed.unpack_records(buf)
+    idx[3], cost[3], X[3], reproj[3] = -1, float('nan'), float('nan'), float('nan')
     assert torch.equal(got['idx'], idx) and torch.equal(got['n'], n)
     assert torch.equal(got['cost'].view(torch.int32), cost.view(torch.int32))
     assert torch.equal(got['X'].view(torch.int64), X.view(torch.int64))
+    assert torch.equal(got['reproj'].view(torch.int64), reproj.view(torch.int64))
 
 
 @pytest.mark.timeout(120)
@@ -75,10 +81,11 @@ def test_two_rank_gather_equals_single_process(tmp_path):
     total, K, world = 64, 5, 2
     port = _free_port()
     mp.spawn(_worker, args=(world, port, total, K, str(tmp_path)), nprocs=world, join=True)
-    want = distributed.unpack_records(distributed.pack_records(*_fake_results(0, total, K)))
+    want = distributed.unpack_records(distributed.pack_records_torch(*_fake_results(0, total, K)))
     for rank in range(world):
         got = torch.load(os.path.join(str(tmp_path), f'rank{rank}.pt'))
         for key in ('idx', 'n'):
             assert torch.equal(got[key], want[key]), (rank, key)
         assert torch.equal(got['cost'].view(torch.int32), want['cost'].view(torch.int32))
         assert torch.equal(got['X'].view(torch.int64), want['X'].view(torch.int64))
+        assert torch.equal(got['reproj'].view(torch.int64), want['reproj'].view(torch.int64))

@@ -110,6 +110,31 @@ def test_large_boxes_four_to_six_taps(T, width):
         assert np.array_equal(outf[r], wantf), (r, tuple(rois[r]))
 
 
+@pytest.mark.parametrize('T', [320, 512, 1000])
+def test_target_sizes_above_256(T):
+    """The reference's target_size is a free parameter (data_utils.py:34): T up to BPC_MAX_TARGET, every regime and class."""
+    from bpc_baseline_b200 import batched, synth
+    imgs = synth.make_images(2, seed=21, width=1920, height=1080)
+    rng = np.random.default_rng([41, T])
+    rois = [(1, 0, 0, 1920, 1080), (0, 0, 0, min(T, 1080), min(T, 1080)), (1, 1920 - 2 * min(T, 540), 0, 1920, 2 * min(T, 540))]
+    for lo, hi in ((0.1, 0.6), (0.6, 1.0), (1.0, 1.5), (1.5, 2.0), (2.0, 3.3)):
+        for _ in range(5):
+            long_side = max(8, min(int(rng.uniform(lo, hi) * T), 1080))
+            short = int(rng.integers(max(4, long_side // 5), long_side + 1))
+            w, h = (long_side, short) if rng.random() < 0.5 else (short, long_side)
+            x1 = int(rng.integers(0, 1920 - w + 1)); y1 = int(rng.integers(0, 1080 - h + 1))
+            rois.append((int(rng.integers(0, 2)), x1, y1, x1 + w, y1 + h))
+    rois = np.asarray(rois, np.int32)
+    out = batched.roi_crop_u8(to_dev(imgs), to_dev(rois), T=T).cpu().numpy()
+    outf = batched.roi_crop(to_dev(imgs), to_dev(rois), T=T, swap_rb=True).cpu().numpy()
+    lut = batched.normalise_lut('cuda').cpu().numpy()
+    for r, (b, x1, y1, x2, y2) in enumerate(rois):
+        want = ocrop.crop_u8_ref(imgs[b], (x1, y1, x2, y2), T)
+        assert np.array_equal(out[r], want), (r, tuple(rois[r]))
+        wantf = np.stack([lut[p][want[..., 2 - p]] for p in range(3)])
+        assert np.array_equal(outf[r], wantf), (r, tuple(rois[r]))
+
+
 @pytest.mark.parametrize('width', [16, 64, 176, 192, 208, 256])
 def test_small_images_with_16_byte_pitch(width):
     """Image rows of 48 .. 768 bytes, all multiples of 16: below 576 bytes (the widest staging box) the 1-D copy path is

@@ -36,6 +36,44 @@ def test_detections_from_yolo_matches_reference_loop():
     assert overflow >= 0
 
 
+def test_detect_against_the_reference_method(golden_detect):
+    """Kernel and PoseEstimator._detect mirror against outputs of the reference's own _detect (tests/golden/detect.npz)."""
+    from types import SimpleNamespace
+    from bpc_baseline_b200 import batched
+    from bpc_baseline_b200.inference.process_pose import PoseEstimator, PoseEstimatorParams
+    g = golden_detect
+    xyxy, conf, cls, nraw, thresh = g['xyxy'], g['conf'], g['cls'], g['nraw'], float(g['thresh'])
+    S, _, N, _ = xyxy.shape
+    boxes, centers, counts = batched.detections_from_yolo(to_dev(xyxy), to_dev(conf), to_dev(cls), to_dev(nraw), thresh, N)
+    boxes, centers, counts = boxes.cpu().numpy(), centers.cpu().numpy(), counts.cpu().numpy()
+    for s in range(S):
+        for c in range(3):
+            want_b, want_c = g[f'bbox_{s}_{c}'], g[f'center_{s}_{c}']
+            assert counts[s, c] == len(want_b), (s, c)
+            assert np.array_equal(boxes[s, c, :len(want_b)], want_b) and np.array_equal(centers[s, c, :len(want_b)], want_c)
+
+    class _Boxes:
+        def __init__(self, b, c, k):
+            self.xyxy, self.conf, self.cls = torch.from_numpy(b), torch.from_numpy(c), torch.from_numpy(k)
+
+        def __len__(self):
+            return int(self.xyxy.shape[0])
+
+    for s in range(S):
+        calls = iter(range(3))
+
+        def yolo(image, imgsz=1280, _s=s, _calls=calls):
+            c = next(_calls)
+            n = nraw[_s, c]
+            return [SimpleNamespace(boxes=_Boxes(xyxy[_s, c, :n].copy(), conf[_s, c, :n].copy(), cls[_s, c, :n].copy()))]
+
+        est = PoseEstimator(PoseEstimatorParams(yolo_conf_thresh=thresh), yolo=yolo)
+        out = est._detect(SimpleNamespace(images=[np.zeros((4, 4, 3), np.uint8)] * 3))
+        for c in range(3):
+            assert [d['bbox'] for d in out[c]] == [tuple(int(v) for v in b) for b in g[f'bbox_{s}_{c}']]
+            assert [d['bb_center'] for d in out[c]] == [tuple(float(v) for v in b) for b in g[f'center_{s}_{c}']]
+
+
 def test_crops_feed_simple_pose_net_batched():
     """_estimate_rotation end to end with the reference's network architecture (random weights, no download)."""
     from types import SimpleNamespace

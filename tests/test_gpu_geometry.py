@@ -176,9 +176,26 @@ def test_rejects_cpu_tensors_and_missing_library():
         batched.fundamental(torch.zeros(1, 3, 3, 3), torch.zeros(1, 3, 4, 4, dtype=torch.float64))
 
 
+def test_skewed_intrinsics_golden(golden_skew):
+    """K with skew or a general 3x3 (tests/golden/skew.npz, recorded from the reference): np.linalg.inv computes in
+    float64 and rounds to float32, and so does the kernel -- F to 1e-12, float32 costs bit-equal, same matches."""
+    from bpc_baseline_b200 import batched
+    scenes = [golden_skew.scene(n) for n in golden_skew.names]
+    Ks, RTs, centers, boxes, counts = pack_scenes(scenes)
+    out = _run(Ks, RTs, centers, counts)
+    cost = batched.cost_tensor(to_dev(out['F']), to_dev(centers), to_dev(counts)).cpu().numpy()
+    for s, sc in enumerate(scenes):
+        ref = sc['ref']
+        n = int(out['n'][s])
+        np.testing.assert_allclose(out['F'][s], ref['F'], rtol=1e-12, atol=0, err_msg=sc['name'])
+        assert n == len(ref['idx']) and np.array_equal(out['idx'][s, :n], ref['idx']), sc['name']
+        N, M, P = sc['counts']
+        assert np.array_equal(cost[s, :N, :M, :P].view(np.uint32), ref['cost'].view(np.uint32)), sc['name']
+        assert rel_err(out['X'][s, :n], ref['X']).max() < 1e-9, sc['name']
+
+
 def test_skewed_intrinsics_general_inverse():
-    """K with skew takes the general float32 inverse (Gauss-Jordan; LAPACK's last bit is not guaranteed):
-    F within 1e-5 relative of the reference formula, same matches on clean scenes."""
+    """Many more skewed scenes against the oracle (which calls np.linalg.inv like the reference)."""
     from bpc_baseline_b200 import batched, synth
     batch = synth.make_scenes(16, 8, seed=synth.SEED + 61)
     batch.Ks[:, :, 0, 1] = np.float32(3.5)                     # skew
@@ -188,8 +205,95 @@ def test_skewed_intrinsics_general_inverse():
     for s in range(16):
         Kl, RTl = batch.capture_arrays(s)
         want = og.match_scene(Kl, RTl, [batch.centers[s, c, :batch.counts[s, c]] for c in range(3)], 30)
-        np.testing.assert_allclose(F[s], want['F'], rtol=1e-5, atol=1e-9)
+        np.testing.assert_allclose(F[s], want['F'], rtol=1e-12, atol=0)
         assert int(n[s]) == len(want['idx']) and np.array_equal(idx[s, :n[s]], want['idx'])
+
+
+def test_reprojection_filter(golden_scenes):
+    """Optional reproj_thresh (a9): off = the reference's _match; on = drop a match when any view's
+    compute_reprojection_error (utils/triangulation.py:14-18) exceeds it, order of the survivors kept."""
+    from bpc_baseline_b200 import batched
+    scenes = [golden_scenes.scene(n) for n in golden_scenes.names]
+    Ks, RTs, centers, boxes, counts = pack_scenes(scenes)
+    args = (to_dev(Ks), to_dev(RTs), to_dev(centers), to_dev(counts), 30)
+    base = batched.match_triangulate(*args)
+    allrep = np.concatenate([sc['ref']['reproj'].reshape(-1, 3) for sc in scenes])
+    thr = float(np.median(allrep.max(axis=1)))                     # drops about half of the matches
+    for t, expect_all in ((1e9, True), (thr, False), (0.0, False)):
+        res = batched.match_triangulate(*args, reproj_thresh=t)
+        dropped = 0
+        for s, sc in enumerate(scenes):
+            ref = sc['ref']
+            keep = ~(ref['reproj'] > t).any(axis=1) if len(ref['idx']) else np.zeros(0, bool)
+            n = int(res.n[s])
+            assert n == int(keep.sum()), (sc['name'], t)
+            assert np.array_equal(res.idx[s, :n].cpu().numpy(), ref['idx'][keep])
+            assert np.all(res.idx[s, n:].cpu().numpy() == -1) and np.isnan(res.X[s, n:].cpu().numpy()).all()
+            if n:
+                want_cost = ref['cost'][tuple(ref['idx'][keep].T)]
+                assert np.array_equal(res.cost[s, :n].cpu().numpy().view(np.uint32), want_cost.view(np.uint32))
+                assert rel_err(res.X[s, :n].cpu().numpy(), ref['X'][keep]).max() < 1e-9
+                np.testing.assert_allclose(res.reproj[s, :n].cpu().numpy(), ref['reproj'][keep], rtol=1e-6, atol=1e-7)
+            dropped += len(ref['idx']) - n
+        if expect_all:
+            assert dropped == 0 and torch.equal(res.idx, base.idx) and torch.equal(res.n, base.n)
+        else:
+            assert dropped > 0
+
+
+def test_counts_above_dmax_are_reported_not_dropped():
+    """A scene whose count exceeds Dmax (the overflow count of bpc_detections_from_yolo) gets n = -2, not a silent 0."""
+    from bpc_baseline_b200 import batched, synth
+    batch = synth.make_scenes(4, 6, seed=synth.SEED + 63)
+    Ks, RTs, centers, boxes, counts = batch_to_dev(batch)
+    counts = counts.clone()
+    counts[2, 1] = 7
+    res = batched.match_triangulate(Ks, RTs, centers, counts, 30)
+    n = res.n.cpu().numpy()
+    assert n[2] == batched.N_OVERFLOW and (n[[0, 1, 3]] == 6).all()
+    with pytest.raises(RuntimeError, match='exceed Dmax'):
+        batched.check_match_status(res.n)
+
+
+def test_large_dmax_uses_the_workspace():
+    """Dmax beyond what fits shared memory (~450): the scene state moves to the caller's workspace; same results."""
+    from bpc_baseline_b200 import _lib, batched, synth
+    D = 24
+    batch = synth.make_scenes(3, D, seed=synth.SEED + 64, p_drop=0.1, sigma=2.0)
+    Dbig = 520
+    assert _lib.load().bpc_match_workspace_bytes(3, Dbig) > 0
+    centers = np.zeros((3, 3, Dbig, 2)); centers[:, :, :batch.centers.shape[2]] = batch.centers
+    res = batched.match_triangulate(to_dev(batch.Ks), to_dev(batch.RTs), to_dev(centers), to_dev(batch.counts), 30)
+    small = batched.match_triangulate(*batch_to_dev(batch)[:3], to_dev(batch.counts), 30)
+    n = small.n.cpu().numpy()
+    assert np.array_equal(res.n.cpu().numpy(), n)
+    for s in range(3):
+        assert torch.equal(res.idx[s, :n[s]], small.idx[s, :n[s]])
+        assert torch.equal(res.X[s, :n[s]], small.X[s, :n[s]]) and torch.equal(res.cost[s, :n[s]], small.cost[s, :n[s]])
+        Kl, RTl = batch.capture_arrays(s)
+        want = og.match_scene(Kl, RTl, [batch.centers[s, c, :batch.counts[s, c]] for c in range(3)], 30)
+        assert np.array_equal(res.idx[s, :n[s]].cpu().numpy(), want['idx'])
+
+
+def test_pack_records_kernel_equals_layout_spec(golden_scenes):
+    """bpc_pack_records against the torch statement of the layout, byte for byte, and the unpack round trip."""
+    from bpc_baseline_b200 import batched, distributed
+    scenes = [golden_scenes.scene(n) for n in golden_scenes.names]
+    Ks, RTs, centers, boxes, counts = pack_scenes(scenes)
+    res = batched.match_triangulate(to_dev(Ks), to_dev(RTs), to_dev(centers), to_dev(counts), 30)
+    ios = to_dev(np.zeros((len(scenes), 3), np.int32))
+    _, offs = batched.build_rois(to_dev(boxes), res.idx, res.n, ios)
+    buf = distributed.pack_records(res, offs, 3)
+    want = distributed.pack_records_torch(res.idx, res.n, res.cost, res.X, res.reproj)
+    total = int(res.n.clamp(min=0).sum())
+    used = distributed.records_bytes(len(scenes), res.idx.shape[1]) - (len(scenes) * res.idx.shape[1] - total) * 64
+    assert torch.equal(buf[:used], want[:used])
+    got = distributed.unpack_records(buf)
+    assert torch.equal(got['idx'], res.idx) and torch.equal(got['n'], res.n)
+    assert torch.equal(got['X'].view(torch.int64), res.X.view(torch.int64))
+    assert torch.equal(got['reproj'].view(torch.int64), res.reproj.view(torch.int64))
+    assert torch.equal(got['cost'].view(torch.int32), res.cost.view(torch.int32))
+    assert torch.equal(distributed.unpack_records(distributed.pack_records(res))['idx'], res.idx)     # offsets computed inside
 
 
 @pytest.mark.parametrize('threshold', [0.5, 2.25, 12.5, 1e9])

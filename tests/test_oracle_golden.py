@@ -35,6 +35,41 @@ def test_geometry_scene(golden_scenes, name):
         np.testing.assert_array_equal(res['cost'], cost[tuple(res['idx'].T)])
 
 
+def test_skewed_intrinsics(golden_skew):
+    """K with skew / a general 3x3: np.linalg.inv computes in float64 and rounds the result to float32."""
+    for name in golden_skew.names:
+        sc = golden_skew.scene(name)
+        ref = sc['ref']
+        res = og.match_scene(sc['Ks'], sc['RTs'], sc['centers'], threshold=30)
+        np.testing.assert_allclose(res['F'], ref['F'], rtol=1e-12, atol=0)
+        assert np.array_equal(res['idx'], ref['idx'])
+        np.testing.assert_allclose(res['X'], ref['X'], rtol=1e-9, atol=1e-9)
+        Kinv = golden_skew.z[f'{name}/ref_Kinv']
+        for c in range(3):
+            exact = np.linalg.inv(sc['Ks'][c].astype(np.float64)).astype(np.float32)
+            assert np.array_equal(exact.view(np.uint32), Kinv[c].view(np.uint32))
+
+
+def test_detect_restatement(golden_detect):
+    """oracle.detect against PoseEstimator._detect itself (process_pose.py:113-142, run unbound on a fake detector)."""
+    from oracle import detect as odet
+    g = golden_detect
+    S = g['nraw'].shape[0]
+    kept = 0
+    for s in range(S):
+        for c in range(3):
+            n = int(g['nraw'][s, c])
+            got = odet.detections_from_yolo(g['xyxy'][s, c, :n], g['conf'][s, c, :n], g['cls'][s, c, :n], float(g['thresh']))
+            assert len(got) == len(g[f'bbox_{s}_{c}'])
+            for d, det in enumerate(got):
+                assert det['bbox'] == tuple(int(v) for v in g[f'bbox_{s}_{c}'][d])
+                assert det['bb_center'] == tuple(float(v) for v in g[f'center_{s}_{c}'][d])
+            kept += len(got)
+    assert kept > 50 and len(g['bbox_2_0']) == 0 and len(g['bbox_3_0']) == 0
+    assert tuple(g['bbox_0_0'][0]) == (0, -1, 10, 20) or g['cls'][0, 0, 0] != 0     # int() truncates toward zero
+    assert len(g['bbox_0_0']) >= int((g['cls'][0, 0, :6] == 0).sum())                # conf == thresh is kept
+
+
 def test_cost_tensor_equals_loop(golden_scenes):
     """the separable restatement is bit-identical to the reference's triple loop."""
     for name in ('clean10_0', 'drop12_1', 'dup8_0', 'tiny3_3'):
