@@ -53,5 +53,37 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB
     return out
 
 
+EXT = os.path.join(HERE, '_C.so')
+EXT_SRC = os.path.join(CSRC, 'torch_ext.cpp')
+
+
+def build_torch_ext(force: bool = False, verbose: bool = False) -> str:
+    """bpc_baseline_b200/_C.so: the thin PyTorch C++ extension (csrc/torch_ext.cpp, torch.ops.bpc_b200.*) over the C ABI.
+
+    Compiled in-tree with g++ against torch's headers and linked against libbpc_b200.so next to it (rpath $ORIGIN) --
+    host code only, every kernel stays in libbpc_b200.so."""
+    lib = build(force=force, verbose=verbose)
+    deps = [EXT_SRC, os.path.join(ROOT, 'include', 'bpc_b200.h')]
+    if not force and os.path.exists(EXT) and all(os.path.getmtime(d) <= os.path.getmtime(EXT) for d in deps):
+        return EXT
+    import torch
+    from torch.utils import cpp_extension as ce
+    cuda_home = os.path.dirname(os.path.dirname(nvcc_path()))
+    inc = [p for p in ce.include_paths() if os.path.isdir(p)] + [os.path.join(cuda_home, 'include'), os.path.join(ROOT, 'include')]
+    libdirs = [os.path.join(os.path.dirname(torch.__file__), 'lib'), os.path.join(cuda_home, 'lib64')]
+    cmd = ['g++', '-shared', '-fPIC', '-O2', '-std=c++17', f'-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}',
+           '-DTORCH_API_INCLUDE_EXTENSION_H', *[f'-I{p}' for p in inc], EXT_SRC, '-o', EXT,
+           *[f'-L{d}' for d in libdirs], f'-L{HERE}', '-l:' + os.path.basename(lib),
+           '-lc10', '-lc10_cuda', '-ltorch_cpu', '-ltorch_cuda', '-ltorch', '-lcudart',
+           '-Wl,-rpath,$ORIGIN', *[f'-Wl,-rpath,{d}' for d in libdirs]]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError('g++ failed building _C.so')
+    return EXT
+
+
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='--verbose' in sys.argv))
+    print(build_torch_ext(force='--force' in sys.argv, verbose='--verbose' in sys.argv))

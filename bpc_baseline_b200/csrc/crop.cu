@@ -71,6 +71,9 @@ static_assert(sizeof(RoiGeom) == 88, "RoiGeom layout");
 // per staging pitch, box = {pitch / 4 words, 4 rows} (2 rows for the two widest), so one TMA instruction stages four
 // source rows of a strip instead of one bulk copy per row; rows / columns beyond the pool are zero-filled by the TMA
 // unit, which removes the guarded tail path.
+#ifndef BPC_L2_PROMO
+#define BPC_L2_PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+#endif
 constexpr int N_TMAPS = 15;
 constexpr int N_TMAPS8 = 8;                  // 8-row boxes for the streaming class-1 path: pitches 64 .. 288
 struct TmapSet { CUtensorMap m[N_TMAPS]; CUtensorMap m8[N_TMAPS8]; };
@@ -1255,7 +1258,7 @@ static int tensor_maps(const uint8_t* images, int B, int H, int W, bool aligned,
         const int pitch = i < 13 ? 64 + 32 * i : 512 + 64 * (i - 13);
         const cuuint32_t box[2] = {(cuuint32_t)pitch / 4, (cuuint32_t)tmap_rows(pitch)};
         const CUresult r = encode(&cached.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)images, gdim, gstride, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, BPC_L2_PROMO,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { k_images = nullptr; return (int)cudaErrorInvalidValue; }
     }
@@ -1263,7 +1266,7 @@ static int tensor_maps(const uint8_t* images, int B, int H, int W, bool aligned,
         const int pitch = 64 + 32 * i;
         const cuuint32_t box[2] = {(cuuint32_t)pitch / 4, (cuuint32_t)STREAM_ROWS};
         const CUresult r = encode(&cached.m8[i], CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, (void*)images, gdim, gstride, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, BPC_L2_PROMO,
                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { k_images = nullptr; return (int)cudaErrorInvalidValue; }
     }

@@ -736,6 +736,7 @@ __global__ void bpc_pack_records_kernel(const int32_t* __restrict__ idx, const i
     int32_t* head = reinterpret_cast<int32_t*>(buf);
     if (t == 0) { head[0] = scene_offset[S] / offset_div; head[1] = S; head[2] = Kmax; head[3] = 0; }
     if (t < S) head[4 + t] = n[t];
+    else if (t < ((S + 3) & ~3)) head[4 + t] = 0;             // padding of the counts up to the 16-byte record base
     if (t >= (long long)S * Kmax) return;
     const int s = (int)(t / Kmax), m = (int)(t - (long long)s * Kmax);
     if (m >= n[s]) return;

@@ -17,20 +17,27 @@ import numpy as np
 import torch
 
 from . import batched
+from ._host import nvtx_range
 
 
 class MatchCropPipeline:
     def __init__(self, S: int, Dmax: int, *, T: int = 224, chunk_rois: int = 16384, threshold=30,
-                 swap_rb: bool = True, fill=(255, 255, 255), device='cuda', want_reproj: bool = True):
+                 swap_rb: bool = True, fill=(255, 255, 255), device='cuda', want_reproj: bool = True,
+                 reproj_thresh: Optional[float] = None, crops: Optional[torch.Tensor] = None):
         self.S, self.D, self.T = int(S), int(Dmax), int(T)
         self.device = torch.device(device)
         self.threshold = threshold
-        self.swap_rb, self.fill, self.want_reproj = swap_rb, tuple(fill), want_reproj
+        self.swap_rb, self.fill, self.want_reproj, self.reproj_thresh = swap_rb, tuple(fill), want_reproj, reproj_thresh
         self.cap = self.S * self.D * 3                     # ROI capacity: 3 views x at most Dmax matches
         self.chunk = max(1, min(int(chunk_rois), self.cap))
         dev = self.device
         self.rois = torch.zeros((self.cap, 5), dtype=torch.int32, device=dev)
-        self.crops = torch.empty((self.chunk, 3, self.T, self.T), dtype=torch.float32, device=dev)
+        if crops is not None:                              # a caller-owned chunk buffer shared between pipelines
+            if crops.dtype != torch.float32 or not crops.is_contiguous() or crops.numel() < self.chunk * 3 * self.T * self.T:
+                raise RuntimeError('crops must be a contiguous float32 buffer of at least chunk_rois * 3 * T * T elements')
+            self.crops = crops.view(-1)[:self.chunk * 3 * self.T * self.T].view(self.chunk, 3, self.T, self.T)
+        else:
+            self.crops = torch.empty((self.chunk, 3, self.T, self.T), dtype=torch.float32, device=dev)
         self.status = torch.zeros((self.cap,), dtype=torch.int32, device=dev)
         self.lut = batched.normalise_lut(dev)
         self._host = None
@@ -48,8 +55,11 @@ class MatchCropPipeline:
         ``events``: optional (e_match, e_crop0, e_crop1) CUDA events recorded after the matcher, before
         the first and after the last crop launch.
         """
-        res = batched.match_triangulate(Ks, RTs, centers, counts, self.threshold, want_reproj=self.want_reproj)
-        rois, offs = batched.build_rois(boxes, res.idx, res.n, image_of_scene, rois=self.rois)
+        with nvtx_range('bpc.match'):
+            res = batched.match_triangulate(Ks, RTs, centers, counts, self.threshold, want_reproj=self.want_reproj,
+                                            reproj_thresh=self.reproj_thresh)
+        with nvtx_range('bpc.build_rois'):
+            rois, offs = batched.build_rois(boxes, res.idx, res.n, image_of_scene, rois=self.rois)
         total = offs[self.S:self.S + 1]
         if events is not None:
             events[0].record()
@@ -58,9 +68,10 @@ class MatchCropPipeline:
         launches = 0
         for first in range(0, upto, self.chunk):
             r = min(self.chunk, self.cap - first)
-            out = batched.roi_crop(images, rois[first:first + r], T=self.T, fill=self.fill, swap_rb=self.swap_rb,
-                                   lut=self.lut, n_rois=total, roi_first=first, out=self.crops,
-                                   status=self.status[first:first + r])
+            with nvtx_range('bpc.crop_chunk'):
+                out = batched.roi_crop(images, rois[first:first + r], T=self.T, fill=self.fill, swap_rb=self.swap_rb,
+                                       lut=self.lut, n_rois=total, roi_first=first, out=self.crops,
+                                       status=self.status[first:first + r])
             launches += 1
             if consumer is not None:
                 consumer(out[:r], first)

@@ -47,7 +47,7 @@ enum {
 #define BPC_N_OVERFLOW (-2)     /* a camera's count exceeds Dmax (e.g. the overflow count of bpc_detections_from_yolo) */
 
 /* limits */
-#define BPC_MAX_DET 2048        /* Dmax <= 2048 detections per camera; a scene stays in shared memory up to Dmax ~ 450,
+#define BPC_MAX_DET 2048        /* Dmax <= 2048 detections per camera; a scene stays in shared memory up to Dmax ~ 550,
                                    larger scenes keep their state in the caller's workspace (bpc_match_workspace_bytes) */
 #define BPC_MAX_ROI_WIDTH 8192  /* widest source box the crop kernel stages in shared memory */
 #define BPC_MAX_TARGET 1024     /* crop target size T <= 1024 (one thread per output column in the generic kernel) */
@@ -109,7 +109,7 @@ int bpc_match_objects(const float* cost, int S, int N, int M, int P, float thres
  *   reproj double [S][Kmax][3]  reprojection error per view, pixels (NaN padded); may be NULL
  *   F      double [S][3][3][3]  fundamental matrices; may be NULL
  * Workspace: bpc_match_workspace_bytes(S, Dmax) bytes, 16-byte aligned: 0 while a scene fits shared memory (Dmax up to
- * ~450), else one state block per resident CTA (the kernel then walks the scenes with a fixed grid).
+ * ~550), else one state block per resident CTA (the kernel then walks the scenes with a fixed grid).
  */
 size_t bpc_match_workspace_bytes(int S, int Dmax);
 int bpc_match_triangulate(const float* Ks, const double* RTs, const double* centers, const int32_t* counts,

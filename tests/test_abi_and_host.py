@@ -195,3 +195,25 @@ def test_rotation_decode_and_pose_assembly_match_reference():
             assert np.allclose(calc_pose_matrix(final, g['t'][r]), g[f'pose_{mode}'][r], rtol=0, atol=1e-3)
         # batched decode == the reference's one-at-a-time decode, to float32 rounding of the batched torch ops
         assert np.abs(np.stack([g['cam_R'][r].T @ rot[r] for r in range(len(rot))]) - g[f'final_{mode}']).max() < 2e-6
+
+
+def test_torch_extension_loads_and_registers_its_operators():
+    """bpc_baseline_b200/_C.so (csrc/torch_ext.cpp): loads without a GPU, links the same ABI version, registers every
+    operator with a schema, and its Meta kernels give shapes / dtypes without running anything."""
+    import torch
+    from bpc_baseline_b200 import build, ops
+    build.build_torch_ext()
+    o = ops.load()
+    assert int(o.abi_version()) == 2
+    for name in ('match_triangulate', 'box_centers', 'build_rois', 'normalise_lut', 'roi_crop', 'roi_crop_u8', 'pack_records', 'fundamental'):
+        assert hasattr(o, name), name
+    meta = lambda shape, dt: torch.empty(shape, dtype=dt, device='meta')
+    r = o.match_triangulate(meta((4, 3, 3, 3), torch.float32), meta((4, 3, 4, 4), torch.float64), meta((4, 3, 9, 2), torch.float64),
+                            meta((4, 3), torch.int32), 30.0, None, True)
+    assert [tuple(t.shape) for t in r] == [(4, 9, 3), (4,), (4, 9), (4, 9, 3), (4, 9, 3), (4, 3, 3, 3)]
+    rois, offs = o.build_rois(meta((4, 3, 9, 4), torch.int32), r[0], r[1], meta((4, 3), torch.int32))
+    assert tuple(rois.shape) == (4 * 9 * 3, 5) and tuple(offs.shape) == (5,)
+    crops, status = o.roi_crop(meta((2, 64, 64, 3), torch.uint8), rois, 32, [255, 255, 255], True, meta((3, 256), torch.float32), None, 0, None)
+    assert tuple(crops.shape) == (108, 3, 32, 32) and crops.dtype == torch.float32 and tuple(status.shape) == (108,)
+    with pytest.raises(NotImplementedError):            # no CPU kernel: a CPU tensor cannot fall back to anything
+        o.box_centers(torch.zeros((3, 4), dtype=torch.int32))
