@@ -36,20 +36,44 @@ def stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
-    """``defines`` / ``out``: experiment builds (e.g. -DBPC_STG_CS into another file, selected with BPC_LIB)."""
+    """``defines`` / ``out``: experiment builds (e.g. -DBPC_STG_CS into another file, selected with BPC_LIB).
+
+    One object file per translation unit under build/obj (compiled in parallel, reused while the source, the headers and the
+    defines are unchanged), then one link."""
     if not force and not stale() and out == LIB:
         return LIB
-    cmd = [nvcc_path(), '-shared', '-Xcompiler', '-fPIC', '-O3', '-std=c++17', '-lineinfo', '--fmad=false', '--threads', '4',
-           *ARCH, '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
+    import hashlib
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(ROOT, 'build', 'obj')
+    os.makedirs(objdir, exist_ok=True)
+    tag = hashlib.sha1(' '.join(sorted(defines)).encode()).hexdigest()[:8]
+    base = [nvcc_path(), '-Xcompiler', '-fPIC', '-O3', '-std=c++17', '-lineinfo', '--fmad=false',
+            *ARCH, '-I', os.path.join(ROOT, 'include'), '-I', CSRC]
     if verbose:
-        cmd += ['-Xptxas', '-v']
-    cmd += [f'-D{d}' for d in defines]
-    cmd += [os.path.join(CSRC, f) for f in SOURCES] + ['-o', out]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
+        base += ['-Xptxas', '-v']
+    base += [f'-D{d}' for d in defines]
+    hdrs = [os.path.join(CSRC, f) for f in HEADERS] + [os.path.join(ROOT, 'include', 'bpc_b200.h')]
+
+    def compile_one(name):
+        src = os.path.join(CSRC, name)
+        obj = os.path.join(objdir, f'{os.path.splitext(name)[0]}-{tag}.o')
+        newest = max(os.path.getmtime(d) for d in [src] + hdrs)
+        if not force and not verbose and os.path.exists(obj) and os.path.getmtime(obj) > newest:
+            return obj, None
+        res = subprocess.run(base + ['-c', src, '-o', obj], capture_output=True, text=True)
+        return obj, res
+
+    with ThreadPoolExecutor(len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    for obj, res in results:
+        if res is not None and (verbose or res.returncode != 0):
+            sys.stderr.write(res.stdout + res.stderr)
+        if res is not None and res.returncode != 0:
+            raise RuntimeError(f'nvcc failed compiling {obj}')
+    res = subprocess.run([nvcc_path(), '-shared', *ARCH, *[o for o, _ in results], '-o', out], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError('nvcc failed building libbpc_b200.so')
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError('nvcc failed linking libbpc_b200.so')
     return out
 
 

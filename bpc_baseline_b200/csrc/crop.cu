@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256)
 bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const int32_t* __restrict__ rois, int R,
                      const int32_t* __restrict__ n_rois_dev, int roi_first, int T, int stream_ok,
                      RoiGeom* __restrict__ geom, float4* __restrict__ xdesc, float4* __restrict__ ydesc,
-                     int32_t* __restrict__ glist, int32_t* __restrict__ gcount, int32_t* __restrict__ status) {
+                     int32_t* __restrict__ glist, int32_t* __restrict__ gcount, int32_t* __restrict__ status, int32_t* __restrict__ list1) {
     __shared__ RoiGeom g;
     __shared__ int s_bad;
     const int roi = blockIdx.x, tid = threadIdx.x;
@@ -303,6 +303,7 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
     __syncthreads();
     if (tid == 0) {
         if (g.cls == 2) glist[atomicAdd(gcount, 1)] = roi;
+        if (g.cls == 1 && list1 != nullptr) list1[atomicAdd(gcount + 8, 1)] = roi;      // streamed by bpc_crop_cta_kernel
         geom[roi] = g;
     }
 }
@@ -419,8 +420,21 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr) {
 }
 
 // output store of the fast paths: the crop buffer is written once and never re-read by this kernel
+#if defined(BPC_WHATIF)
+__device__ float* g_whatif_base;
+#endif
+template <int K = 0>
 __device__ __forceinline__ void stg_out(float* p, float v) {
-#ifdef BPC_STG_CS
+#if defined(BPC_WHATIF) && BPC_WHATIF == 1          // only plane 0 is stored
+    if (K == 0) *p = v; else asm volatile("" :: "f"(v));
+#elif defined(BPC_WHATIF) && BPC_WHATIF == 2        // LSU traffic without L2 traffic: the value goes to shared memory
+    asm volatile("st.shared.f32 [%0], %1;" :: "r"(((unsigned)(size_t)p) & 0x7cu), "f"(v));
+#elif defined(BPC_WHATIF) && BPC_WHATIF == 4        // stores fold into a 128 KB window per CTA (57 MB in all: stays in L2)
+    float* q = (float*)((size_t)g_whatif_base + ((size_t)blockIdx.x << 17) + (((size_t)p) & 0x1fffc));
+    *q = v;
+#elif defined(BPC_WHATIF) && BPC_WHATIF == 3        // no store, LUT value still loaded
+    asm volatile("" :: "f"(v));
+#elif defined(BPC_STG_CS)
     __stcs(p, v);
 #else
     *p = v;
@@ -567,9 +581,11 @@ __global__ void __launch_bounds__(256, 3)
 bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom,
                      const float4* __restrict__ xdesc, const float4* __restrict__ ydesc, int32_t* __restrict__ wcount,
                      int R, int Trt, int nslot, uchar4 fill, int swap_rb, const float* __restrict__ lut_g,
-                     float* __restrict__ outf, uint8_t* __restrict__ outb, const __grid_constant__ TmapSet tm, int dbg) {
+                     float* __restrict__ outf, uint8_t* __restrict__ outb, const __grid_constant__ TmapSet tm) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* lut = reinterpret_cast<float*>(smem);                                 // [3][LUT_STRIDE]: 256 values + the fill value
+    const int skip_cls1 = swap_rb & 0x100;           // class 1 is streamed by bpc_crop_cta_kernel in this call
+    swap_rb &= 0xff;
     const int T = TT ? TT : Trt;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     unsigned char* wbase = smem + LUT_SMEM + wid * WARP_SMEM;         // [2][WARP_BUF] staging, then [2][32] float4 row descriptors
@@ -582,7 +598,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
     if (lane < 8) mbar_init(bar_s + 8 * lane, 1);
     unsigned ph = 0;                                                      // bit j: parity of the next completion of barrier j
     if (!OUT_U8)
-        for (int e = tid; e < 768; e += 256) lut[(e >> 8) * LUT_STRIDE + (e & 255)] = lut_g[e];
+        for (int e = tid; e < 768; e += (int)blockDim.x) lut[(e >> 8) * LUT_STRIDE + (e & 255)] = lut_g[e];
     __syncthreads();
     Out<OUT_U8> out;
     out_init(out, outf, outb, lut, T, swap_rb, fill);
@@ -596,6 +612,44 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
     const unsigned long long img_end = (unsigned long long)(uintptr_t)images + (unsigned long long)B * H * rowstride;
     const float nz = __int_as_float((int)(0x80000000u | (unsigned)fill.w));     // -0.0f: fill.w is 0 at run time
     const u64 nz2 = pack2(nz, nz);
+#if defined(BPC_WHATIF)
+    if (tid == 0) g_whatif_base = outf;
+    __syncthreads();
+#endif
+#ifdef BPC_CTA_ROI
+    // CTA = ROI, warp w = strip w (+ nwarps, ...): the strips of a crop advance together (one CTA barrier per ring slot in the
+    // streaming path), so a whole output row of every plane reaches L2 / DRAM within a short window and neighbouring strips
+    // fetch their overlapping source lines at about the same time.
+    __shared__ int s_roi[2];
+    const int nth = (int)blockDim.x, nwarps = nth >> 5;
+    const int nstrips = (T + 31) >> 5;
+    if (tid == 0) s_roi[0] = atomicAdd(wcount, 1);
+    __syncthreads();
+    for (int it = 0;; ++it) {
+        const int roi = s_roi[it & 1];
+        if (roi >= R) break;
+        int roi_next = 0;
+        if (tid == 0) roi_next = atomicAdd(wcount, 1);          // consumed at the end of this crop: the round trip is hidden
+        const RoiGeom* gp = geom + roi;
+        const int cls = gp->cls;
+        const int new_w = gp->new_w, new_h = gp->new_h, dx0 = gp->dx, dy0 = gp->dy;
+        if (cls == 0) {
+            out.pad_rows(roi, 0, T, tid, nth);
+        } else if (cls == 1 || cls == 3 || cls == 4) {
+            out.pad_rows(roi, 0, dy0, tid, nth);                // whole rows above / below: contiguous runs
+            out.pad_rows(roi, dy0 + new_h, T, tid, nth);
+        }
+        if (cls == 1 || cls == 3 || cls == 4)
+    for (int slot = wid; slot < nstrips; slot += nwarps) {
+        const int nact = min(nwarps, nstrips - (slot - wid));   // warps working in this pass (named-barrier width)
+        const bool touches = slot * 32 < dx0 + new_w && slot * 32 + 32 > dx0;
+        if (!touches && !(ALIGNED && cls == 1)) {
+            const int xp = slot * 32 + lane;                    // a strip beside the resized image: fill
+            if (xp < T)
+                for (int r = 0; r < new_h; ++r) out.pad(roi, dy0 + r, xp);
+            continue;
+        }
+#else
     const long long nitems = (long long)R * nslot;
 
     for (;;) {
@@ -608,7 +662,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
         const int roi = item / nslot, slot = item - roi * nslot;
         const RoiGeom* gp = geom + roi;
         const int cls = gp->cls;
-        if (cls == -1 || cls == 2) continue;
+        if (cls == -1 || cls == 2 || (cls == 1 && skip_cls1)) continue;
         const int new_w = gp->new_w, new_h = gp->new_h, dx0 = gp->dx, dy0 = gp->dy;
 
         if (slot == nslot - 1) {
@@ -626,6 +680,9 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             continue;
         }
         if (cls == 0 || slot * 32 >= dx0 + new_w || slot * 32 + 32 <= dx0) continue;
+        const int nact = 1;
+        const bool touches = true;
+#endif
 
         // ---------------- output columns [32 slot, 32 slot + 32): full 128-byte lines per plane and row ----------------
         const int x = slot * 32 + lane;
@@ -818,15 +875,39 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                     bulk_g2s(dring + 8u * STREAM_ROWS * j, ysrc + 8ull * STREAM_ROWS * c, 8u * STREAM_ROWS, bar_s + 8 * j);
                 }
             };
+#ifdef BPC_CTA_ROI
+            if (!touches) {
+                // a strip beside the resized image keeps pace with its neighbours: per ring slot, the fill value for the output
+                // rows that the slot's source rows complete
+                const float2* yrec = reinterpret_cast<const float2*>(ydesc + (size_t)roi * ystride);
+                float* o = outf + ((size_t)roi * 3 * T + dy0) * T + x;
+                int ydone = 0;
+                for (int c = 0; c < nchunks; ++c) {
+                    asm volatile("bar.sync 1, %0;" :: "r"(nact * 32) : "memory");
+                    const float ba = (lane < STREAM_ROWS) ? yrec[c * STREAM_ROWS + lane].x : 0.f;
+                    const int ndone = __popc(__ballot_sync(0xffffffffu, __float_as_int(ba) < 0));
+                    if (x < T)
+                        for (int r = 0; r < ndone; ++r) {
+                            if (OUT_U8) out.pad(roi, dy0 + ydone + r, x);
+                            else { o[0] = out.padf[0]; o[plane] = out.padf[1]; o[2 * plane] = out.padf[2]; o += T; }
+                        }
+                    ydone += ndone;
+                }
+                continue;
+            }
+#endif
             __syncwarp();                                   // previous item finished with the buffers
             for (int c = 0; c < min(nsl, nchunks); ++c) issue(c, c);
             u64 acc01 = 0ull;
             float acc2 = 0.f;
             unsigned roff = 0;                                // element offset of the open output row from optr
             int yout = 0;
-            const bool store_ok = ((TT && TT % 32 == 0) || x < T) && !(dbg & 2);
+            const bool store_ok = (TT && TT % 32 == 0) || x < T;
             int j = 0;
             for (int c = 0; c < nchunks; ++c) {
+#ifdef BPC_CTA_ROI
+                asm volatile("bar.sync 1, %0;" :: "r"(nact * 32) : "memory");
+#endif
                 mbar_wait(bar_s + 8 * j, (ph >> j) & 1u); ph ^= 1u << j;
                 const unsigned rbase = wbase_s + (unsigned)j * slot_bytes + colc4;
 #pragma unroll
@@ -853,19 +934,13 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                                 if (active) out.px(roi, dy0 + yout, x, round_u8(a0f), round_u8(a1f), round_u8(acc2));
                                 else if (padlane) out.pad(roi, dy0 + yout, x);
                                 ++yout;
-                            } else if (!(dbg & 4)) {
-                                unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
-                                if (dbg & 1) { l0 = l1 = l2 = lut_s + 4 * lane; }
+                            } else {
+                                const unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
                                 if (store_ok) {
                                     float* o = optr + roff;
-                                    if (dbg & 16) o = outf + ((size_t)(o - outf) & (size_t)0x3fffff);     // what-if: L2-resident window
-                                    if (dbg & 8) {                                                        // what-if: no LDS -> STG dependency
-                                        stg_out(o, a0f); stg_out(o + plane, a1f); stg_out(o + 2 * plane, acc2);
-                                    } else {
-                                    stg_out(o, lds_f32(swap ? l2 : l0));
-                                    stg_out(o + plane, lds_f32(l1 + 4 * LUT_STRIDE));
-                                    stg_out(o + 2 * plane, lds_f32((swap ? l0 : l2) + 8 * LUT_STRIDE));
-                                    }
+                                    stg_out<0>(o, lds_f32(swap ? l2 : l0));
+                                    stg_out<1>(o + plane, lds_f32(l1 + 4 * LUT_STRIDE));
+                                    stg_out<2>(o + 2 * plane, lds_f32((swap ? l0 : l2) + 8 * LUT_STRIDE));
                                 }
                                 roff += (unsigned)T;
                             }
@@ -1008,6 +1083,218 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                 }
                 s_lo_cur = s_lo_next;
                 bulk_cur = bulk_next;
+            }
+        }
+    }
+#ifdef BPC_CTA_ROI
+        if (tid == 0) s_roi[(it + 1) & 1] = roi_next;
+        __syncthreads();
+    }
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------------
+// CTA kernel: class 1 (area, <= 3 taps per axis), one crop per CTA, warp-specialised
+// ------------------------------------------------------------------------------------------------------
+// Warps 0 .. NS-1 (NS = T / 32 strips) are the consumers of bpc_crop_warp_kernel's streaming path: one lane per output column,
+// source rows in order, (ba, bb) records per source row.  What changed is who feeds them: the LAST warp is a producer whose
+// lane 0 walks the class-1 list (atomic counter), and per ring slot issues ONE 2-D tensor copy of eight FULL-WIDTH source
+// rows of the crop plus the 64 bytes of their records -- seven times fewer TMA operations than one box per strip, every
+// source byte fetched once per crop, and the ~300-cycle scoreboard wait behind each TMA issue (measured: 13 % of the old
+// kernel's warp time) sits in a warp that has nothing else to do.  The producer runs ahead across crops (ring of four slots,
+// header ring of two crops), which also hides the per-crop set-up round trips.  Consumers meet on the slots' full / empty
+// mbarriers, so the strips of one crop stay within four slots of each other: whole 896-byte output rows of a plane reach L2
+// close together, and the rows above / below the resized image are written as contiguous runs by all consumer threads.
+constexpr int CTA_ROWS = 8;                  // source rows per ring slot (= one TMA box)
+constexpr int CTA_NSLOT = 4;
+constexpr int CTA_NMAPS = 25;                // box widths 64, 128, ... 1600 bytes (8-byte elements)
+constexpr int CTA_MAX_T = 256;               // 8 consumer warps
+struct CtaMaps { CUtensorMap m[CTA_NMAPS]; };
+__host__ __device__ __forceinline__ int cta_pitch_max(int T) { return ((15 + 3 * (2 * T - 1) + 12 + 63) >> 6) << 6; }
+__host__ __device__ __forceinline__ int cta_smem_bytes(int T) { return LUT_SMEM + CTA_NSLOT * CTA_ROWS * cta_pitch_max(T) + CTA_NSLOT * 8 * CTA_ROWS + 256; }
+
+__device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
+
+template <bool OUT_U8, int TT, bool SWAP>
+__global__ void __launch_bounds__(288, 3)
+bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom,
+                    const float4* __restrict__ xdesc, const float4* __restrict__ ydesc, const int32_t* __restrict__ list1,
+                    int32_t* __restrict__ counters, int Trt, uchar4 fill, int swap_rb, const float* __restrict__ lut_g,
+                    float* __restrict__ outf, uint8_t* __restrict__ outb, const __grid_constant__ CtaMaps tm) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* lut = reinterpret_cast<float*>(smem);
+    const int T = TT ? TT : Trt;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int NS = (T + 31) >> 5;                                   // consumer warps; warp NS is the producer
+    const int slot_bytes = CTA_ROWS * cta_pitch_max(T);
+    const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
+    const unsigned ring_s = smem_s + LUT_SMEM;
+    const unsigned rec_s = ring_s + CTA_NSLOT * slot_bytes;        // [CTA_NSLOT][CTA_ROWS] float2
+    const unsigned misc_s = rec_s + CTA_NSLOT * 8 * CTA_ROWS;
+    const unsigned full_s = misc_s, empty_s = misc_s + 8 * CTA_NSLOT, hfull_s = misc_s + 16 * CTA_NSLOT, hempty_s = hfull_s + 16;
+    volatile int* hdr = reinterpret_cast<volatile int*>(smem + (misc_s - smem_s) + 16 * CTA_NSLOT + 32);       // [2] crop index
+    if (tid == 0) {
+        for (int i = 0; i < CTA_NSLOT; ++i) { mbar_init(full_s + 8 * i, 1); mbar_init(empty_s + 8 * i, NS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(hfull_s + 8 * i, 1); mbar_init(hempty_s + 8 * i, NS); }
+        *reinterpret_cast<volatile unsigned*>(smem + 3 * LUT_STRIDE * 4) = smem_s - 4u * 0x4B000000u;              // see lut_addr()
+    }
+    if (!OUT_U8)
+        for (int e = tid; e < 768; e += (int)blockDim.x) lut[(e >> 8) * LUT_STRIDE + (e & 255)] = lut_g[e];
+    __syncthreads();
+    Out<OUT_U8> out;
+    out_init(out, outf, outb, lut, T, swap_rb, fill);
+    if (!OUT_U8 && tid < 3) lut[tid * LUT_STRIDE + 256] = out.padf[tid];
+    __syncthreads();
+    const unsigned lut_m = *reinterpret_cast<volatile unsigned*>(smem + 3 * LUT_STRIDE * 4);
+    const int ds = desc_stride(T), ystride = ds + 8;
+    const unsigned long long rowstride = (unsigned long long)W * 3ull;
+    const int n1 = counters[8];
+    int32_t* work = counters + 12;
+
+    if (wid == NS) {
+        // ------------------------------------ producer ------------------------------------
+        if (lane != 0) return;
+        int idx = atomicAdd(work, 1);
+        unsigned cg = 0;                                            // slots filled so far
+        for (int hi = 0;; ++hi) {
+            const int hb = hi & 1;
+            if (hi >= 2) mbar_wait(hempty_s + 8 * hb, ((hi >> 1) - 1) & 1);
+            if (idx >= n1) {
+                hdr[hb] = -1;
+                mbar_arrive(hfull_s + 8 * hb);
+                break;
+            }
+            const int idx_next = atomicAdd(work, 1);                // round trip hidden behind this crop's copies
+            const int roi = list1[idx];
+            const RoiGeom* gp = geom + roi;
+            const unsigned long long src = gp->src;
+            const int w = gp->w, h = gp->h;
+            hdr[hb] = roi;
+            mbar_arrive(hfull_s + 8 * hb);
+            const int mis0 = (int)(src & 15ull);
+            const int pitch = ((mis0 + 3 * w + 12 + 63) >> 6) << 6;
+            const unsigned long long off = (src & ~15ull) - (unsigned long long)(uintptr_t)images;
+            const int row0 = (int)(off / rowstride);
+            const int x8 = (int)((off - (unsigned long long)row0 * rowstride) >> 3);
+            const CUtensorMap* map = &tm.m[(pitch >> 6) - 1];
+            const unsigned long long yrec = (unsigned long long)(uintptr_t)(ydesc + (size_t)roi * ystride);
+            const int nchunks = (h + CTA_ROWS - 1) / CTA_ROWS;
+            for (int c = 0; c < nchunks; ++c, ++cg) {
+                const unsigned j = cg % CTA_NSLOT;
+                if (cg >= CTA_NSLOT) mbar_wait(empty_s + 8 * j, ((cg / CTA_NSLOT) - 1) & 1);
+                mbar_expect_tx(full_s + 8 * j, (unsigned)(CTA_ROWS * pitch + 8 * CTA_ROWS));
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             :: "r"(ring_s + j * slot_bytes), "l"(map), "r"(x8), "r"(row0 + c * CTA_ROWS), "r"(full_s + 8 * j) : "memory");
+                bulk_g2s(rec_s + 8u * CTA_ROWS * j, yrec + 8ull * CTA_ROWS * c, 8u * CTA_ROWS, full_s + 8 * j);
+            }
+            idx = idx_next;
+        }
+        return;
+    }
+
+    // ------------------------------------ consumers: warp = strip ------------------------------------
+    constexpr bool swap = SWAP;
+    const size_t plane = (size_t)T * T;
+    const float nz = __int_as_float((int)(0x80000000u | (unsigned)fill.w));     // -0.0f: fill.w is 0 at run time
+    const u64 nz2 = pack2(nz, nz);
+    const int nthc = NS * 32;
+    const int x = wid * 32 + lane;
+    unsigned cg = 0;
+    for (int hi = 0;; ++hi) {
+        const int hb = hi & 1;
+        mbar_wait(hfull_s + 8 * hb, (hi >> 1) & 1);
+        const int roi = hdr[hb];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(hempty_s + 8 * hb);
+        if (roi < 0) break;
+        const RoiGeom* gp = geom + roi;
+        const int new_w = gp->new_w, new_h = gp->new_h, dx0 = gp->dx, dy0 = gp->dy, h = gp->h;
+        const int mis0 = (int)(gp->src & 15ull);
+        const int pitch = ((mis0 + 3 * gp->w + 12 + 63) >> 6) << 6;
+        const int nchunks = (h + CTA_ROWS - 1) / CTA_ROWS;
+        out.pad_rows(roi, 0, dy0, tid, nthc);                       // whole rows above / below: contiguous runs
+        out.pad_rows(roi, dy0 + new_h, T, tid, nthc);
+        const int xr = x - dx0;
+        const bool active = xr >= 0 && xr < new_w;
+        const bool touches = wid * 32 < dx0 + new_w && wid * 32 + 32 > dx0;
+        const bool store_ok = (TT && TT % 32 == 0) || x < T;
+        float* optr = outf + ((size_t)roi * 3 * T + dy0) * T + x;     // (plane 0, first image row, column x)
+        if (!touches) {
+            // a strip beside the resized image: the fill value, at the pace of the neighbours
+            int ydone = 0;
+            for (int c = 0; c < nchunks; ++c, ++cg) {
+                const unsigned j = cg % CTA_NSLOT;
+                mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
+                const float ba = (lane < CTA_ROWS) ? lds_f32(rec_s + 8u * CTA_ROWS * j + 8u * lane) : 0.f;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_s + 8 * j);
+                const int ndone = __popc(__ballot_sync(0xffffffffu, __float_as_int(ba) < 0));
+                if (store_ok)
+                    for (int r = 0; r < ndone; ++r) {
+                        if (OUT_U8) out.pad(roi, dy0 + ydone + r, x);
+                        else { optr[0] = out.padf[0]; optr[plane] = out.padf[1]; optr[2 * plane] = out.padf[2]; optr += T; }
+                    }
+                ydone += ndone;
+            }
+            continue;
+        }
+        const float4 xd = xdesc[(size_t)roi * ds + min(max(xr, 0), new_w - 1)];
+        const int xs = __float_as_int(xd.w) & 0xffffff;
+        const int colc = 3 * xs + mis0;
+        const unsigned colc4 = (unsigned)(colc & ~3);
+        const int shc = (colc & 3) * 8;
+        ColW cw;
+        cw.set(xd.x, xd.y, xd.z);
+        if (!active) {                               // beside the image: every row sums to 256 -> LUT entry 256 = fill
+            cw.w[0] = cw.w[1] = cw.w[2] = 0.f;
+            cw.c[0] = 256.f; cw.c[1] = cw.c[2] = 0.f;
+        }
+        u64 acc01 = 0ull;
+        float acc2 = 0.f;
+        unsigned roff = 0;                                // element offset of the open output row from optr
+        int yout = 0;
+        for (int c = 0; c < nchunks; ++c, ++cg) {
+            const unsigned j = cg % CTA_NSLOT;
+            mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
+            const unsigned rbase = ring_s + j * slot_bytes + colc4;
+#pragma unroll
+            for (int half = 0; half < CTA_ROWS / 4; ++half) {
+                const float4 dA = lds_f4(rec_s + 8u * CTA_ROWS * j + 32u * half), dB = lds_f4(rec_s + 8u * CTA_ROWS * j + 32u * half + 16);
+                u64 h01[4];
+                float h2[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) h_area3(rbase + (unsigned)((4 * half + k) * pitch), shc, cw, h01[k], h2[k]);
+                if (half == CTA_ROWS / 4 - 1) {
+                    __syncwarp();                           // every lane has read slot j
+                    if (lane == 0) mbar_arrive(empty_s + 8 * j);
+                }
+                const float ba[4] = {dA.x, dA.z, dB.x, dB.z}, bb[4] = {dA.y, dA.w, dB.y, dB.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float wa = fabsf(ba[k]);
+                    acc01 = fadd2(acc01, fprod2(pack2(wa, wa), h01[k], nz2));
+                    acc2 = __fadd_rn(acc2, __fmul_rn(wa, h2[k]));
+                    if (__float_as_int(ba[k]) < 0) {            // output row complete
+                        float a0f, a1f;
+                        unpack2(acc01, a0f, a1f);
+                        if (OUT_U8) {
+                            if (active) out.px(roi, dy0 + yout, x, round_u8(a0f), round_u8(a1f), round_u8(acc2));
+                            else if (x < T) out.pad(roi, dy0 + yout, x);
+                            ++yout;
+                        } else {
+                            const unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
+                            if (store_ok) {
+                                float* o = optr + roff;
+                                stg_out<0>(o, lds_f32(swap ? l2 : l0));
+                                stg_out<1>(o + plane, lds_f32(l1 + 4 * LUT_STRIDE));
+                                stg_out<2>(o + 2 * plane, lds_f32((swap ? l0 : l2) + 8 * LUT_STRIDE));
+                            }
+                            roff += (unsigned)T;
+                        }
+                        acc01 = fprod2(pack2(bb[k], bb[k]), h01[k], nz2);
+                        acc2 = __fmul_rn(bb[k], h2[k]);
+                    }
+                }
             }
         }
     }
@@ -1275,11 +1562,48 @@ static int tensor_maps(const uint8_t* images, int B, int H, int W, bool aligned,
     return BPC_OK;
 }
 
-// workspace: geom[R] | xdesc[R][ds] | ydesc[R][ds + 8] | counters[16] | glist[R]      (ds = desc_stride(T), float4 records)
+// Tensor maps of the CTA kernel: the pool as [B*H rows][W*3/8 uint64], box = {64 i bytes, CTA_ROWS rows}, i = 1 .. CTA_NMAPS.
+static int cta_tensor_maps(const uint8_t* images, int B, int H, int W, CtaMaps* out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static std::mutex mu;
+    static CtaMaps cached;
+    static const uint8_t* k_images = nullptr;
+    static int k_B = 0, k_H = 0, k_W = 0, k_dev = -1;
+    static EncodeFn encode = nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (images == k_images && B == k_B && H == k_H && W == k_W && dev == k_dev) { *out = cached; return BPC_OK; }
+    if (!encode) {
+        cudaDriverEntryPointQueryResult q;
+        void* fnp = nullptr;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &q);
+        if (e != cudaSuccess) return (int)e;
+        if (q != cudaDriverEntryPointSuccess || !fnp) return (int)cudaErrorNotSupported;
+        encode = (EncodeFn)fnp;
+    }
+    const cuuint64_t gdim[2] = {(cuuint64_t)W * 3 / 8, (cuuint64_t)B * H};
+    const cuuint64_t gstride[1] = {(cuuint64_t)W * 3};
+    const cuuint32_t estr[2] = {1, 1};
+    for (int i = 0; i < CTA_NMAPS; ++i) {
+        const cuuint32_t box[2] = {(cuuint32_t)(8 * (i + 1)), (cuuint32_t)CTA_ROWS};
+        const CUresult r = encode(&cached.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)images, gdim, gstride, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, BPC_L2_PROMO,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { k_images = nullptr; return (int)cudaErrorInvalidValue; }
+    }
+    k_images = images; k_B = B; k_H = H; k_W = W; k_dev = dev;
+    *out = cached;
+    return BPC_OK;
+}
+
+// workspace: geom[R] | xdesc[R][ds] | ydesc[R][ds + 8] | counters[16] | glist[R] | list1[R]    (ds = desc_stride(T), float4 records)
 static size_t ws_off_xdesc(int R) { return (((size_t)R * sizeof(RoiGeom)) + 15) & ~(size_t)15; }
 static size_t ws_off_ydesc(int R, int T) { return ws_off_xdesc(R) + (size_t)R * desc_stride(T) * sizeof(float4); }
 static size_t ws_off_count(int R, int T) { return ws_off_ydesc(R, T) + (size_t)R * (desc_stride(T) + 8) * sizeof(float4); }
-static size_t crop_workspace_bytes(int R, int T) { return ws_off_count(R, T) + 64 + (size_t)R * sizeof(int32_t) + 64; }
+static size_t crop_workspace_bytes(int R, int T) { return ws_off_count(R, T) + 64 + 2 * (size_t)R * sizeof(int32_t) + 64; }
 
 template <bool OUT_U8>
 static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R, const int32_t* n_rois_dev,
@@ -1297,20 +1621,48 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
     RoiGeom* geom = (RoiGeom*)wsb;
     float4* xdesc = (float4*)(wsb + ws_off_xdesc(R));
     float4* ydesc = (float4*)(wsb + ws_off_ydesc(R, T));
-    int32_t* gcount = (int32_t*)(wsb + ws_off_count(R, T));   // [0] generic-list length, [4] warp-item counter
+    int32_t* gcount = (int32_t*)(wsb + ws_off_count(R, T));   // [0] generic-list length, [4] warp-item counter, [8] class-1 list length, [12] its work counter
     int32_t* wcount = gcount + 4;
     int32_t* glist = gcount + 16;
+    int32_t* list1 = glist + R;
     cudaError_t e = cudaMemsetAsync(gcount, 0, 64, st);
     if (e != cudaSuccess) return (int)e;
     // 2-D TMA staging needs a 16-byte image pitch; rows narrower than the widest box keep the 1-D path
     const bool aligned = ((long long)W * 3) % 16 == 0 && (long long)W * 3 >= TMAP_MAX_PITCH;
+    // class 1 through the warp-specialised CTA kernel: 2-D TMA staging, at most eight strips, full-width boxes inside the pool rows
+    const bool use_cta = aligned && T <= CTA_MAX_T && (long long)W * 3 >= cta_pitch_max(T);
     bpc_crop_prep_kernel<<<R, 256, 0, st>>>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, aligned ? 1 : 0, geom, xdesc, ydesc,
-                                            glist, gcount, status);
+                                            glist, gcount, status, use_cta ? list1 : nullptr);
     BPC_LAUNCH_CHECK();
     const uchar4 f4 = make_uchar4(fill[0], fill[1], fill[2], 0);
+    if (use_cta) {
+        typedef void (*CtaFn)(const uint8_t*, int, int, int, const RoiGeom*, const float4*, const float4*, const int32_t*, int32_t*, int,
+                              uchar4, int, const float*, float*, uint8_t*, const CtaMaps);
+        CtaMaps cmaps;
+        const int terr = cta_tensor_maps(images, B, H, W, &cmaps);
+        if (terr != BPC_OK) return terr;
+        const bool sw = swap_rb != 0;
+        CtaFn fn;
+        if (OUT_U8) fn = bpc_crop_cta_kernel<OUT_U8, 0, false>;
+        else if (T == 224) fn = sw ? bpc_crop_cta_kernel<OUT_U8, 224, true> : bpc_crop_cta_kernel<OUT_U8, 224, false>;
+        else if (T == 256) fn = sw ? bpc_crop_cta_kernel<OUT_U8, 256, true> : bpc_crop_cta_kernel<OUT_U8, 256, false>;
+        else fn = sw ? bpc_crop_cta_kernel<OUT_U8, 0, true> : bpc_crop_cta_kernel<OUT_U8, 0, false>;
+        const int smem_bytes = cta_smem_bytes(T);
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cta_smem_bytes(CTA_MAX_T));
+        if (e != cudaSuccess) return (int)e;
+        const int threads = 32 * ((T + 31) / 32 + 1);
+        int dev = 0, sms = 148, per_sm = 3;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem_bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
+        const long long slots = (long long)sms * per_sm;
+        const int grid = (int)((long long)R < slots ? R : slots);
+        fn<<<grid, threads, smem_bytes, st>>>(images, B, H, W, geom, xdesc, ydesc, list1, gcount, T, f4, swap_rb, lut, outf, outb, cmaps);
+        BPC_LAUNCH_CHECK();
+    }
     {
         typedef void (*WarpFn)(const uint8_t*, int, int, int, const RoiGeom*, const float4*, const float4*, int32_t*, int, int, int,
-                               uchar4, int, const float*, float*, uint8_t*, const TmapSet, int);
+                               uchar4, int, const float*, float*, uint8_t*, const TmapSet);
         TmapSet tmaps;
         const int terr = tensor_maps(images, B, H, W, aligned, &tmaps);
         if (terr != BPC_OK) return terr;
@@ -1327,16 +1679,22 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
         // the same constant on every call: idempotent, so concurrent callers cannot interleave set(small) / launch(large)
         e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, WARPK_SMEM);
         if (e != cudaSuccess) return (int)e;
+#ifdef BPC_CTA_ROI
+        const int nstrips = (T + 31) / 32;
+        const int cta_threads = 32 * (nstrips < WARPK_WARPS ? nstrips : WARPK_WARPS);
+        const long long want = R;
+#else
+        const int cta_threads = 256;
         const long long nitems = (long long)R * nslot;
         const long long want = (nitems + WARPK_WARPS - 1) / WARPK_WARPS;
+#endif
         int dev = 0, sms = 148, per_sm = 3;                     // persistent grid: every resident CTA slot, no more
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, 256, WARPK_SMEM) != cudaSuccess || per_sm < 1) per_sm = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, cta_threads, WARPK_SMEM) != cudaSuccess || per_sm < 1) per_sm = 1;
         const long long slots = (long long)sms * per_sm;
         const int grid = (int)(want < slots ? want : slots);
-        static const int dbg = getenv("BPC_CROP_DEBUG") ? atoi(getenv("BPC_CROP_DEBUG")) : 0;
-        fn<<<grid, 256, WARPK_SMEM, st>>>(images, B, H, W, geom, xdesc, ydesc, wcount, R, T, nslot, f4, swap_rb, lut, outf, outb, tmaps, dbg);
+        fn<<<grid, cta_threads, WARPK_SMEM, st>>>(images, B, H, W, geom, xdesc, ydesc, wcount, R, T, nslot, f4, (swap_rb ? 1 : 0) | (use_cta ? 0x100 : 0), lut, outf, outb, tmaps);
         BPC_LAUNCH_CHECK();
     }
     const int nbands = (T + CROP_BAND - 1) / CROP_BAND;
