@@ -303,7 +303,11 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
     __syncthreads();
     if (tid == 0) {
         if (g.cls == 2) glist[atomicAdd(gcount, 1)] = roi;
-        if (g.cls == 1 && list1 != nullptr) list1[atomicAdd(gcount + 8, 1)] = roi;      // streamed by bpc_crop_cta_kernel
+        if (list1 != nullptr) {
+            // crops streamed by bpc_crop_cta_kernel from the front of the list, those of bpc_crop_warp_kernel from its back
+            if (g.cls == 1 || g.cls == 3) list1[atomicAdd(gcount + 8, 1)] = roi;
+            else if (g.cls == 0 || g.cls == 4) list1[R - 1 - atomicAdd(gcount + 9, 1)] = roi;
+        }
         geom[roi] = g;
     }
 }
@@ -581,11 +585,12 @@ __global__ void __launch_bounds__(256, 3)
 bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom,
                      const float4* __restrict__ xdesc, const float4* __restrict__ ydesc, int32_t* __restrict__ wcount,
                      int R, int Trt, int nslot, uchar4 fill, int swap_rb, const float* __restrict__ lut_g,
-                     float* __restrict__ outf, uint8_t* __restrict__ outb, const __grid_constant__ TmapSet tm) {
+                     float* __restrict__ outf, uint8_t* __restrict__ outb, const __grid_constant__ TmapSet tm, const int32_t* __restrict__ wlist) {
     extern __shared__ __align__(128) unsigned char smem[];
     float* lut = reinterpret_cast<float*>(smem);                                 // [3][LUT_STRIDE]: 256 values + the fill value
-    const int skip_cls1 = swap_rb & 0x100;           // class 1 is streamed by bpc_crop_cta_kernel in this call
-    swap_rb &= 0xff;
+    // wlist: the crops of this kernel, stored from the back of the list (the others belong to bpc_crop_cta_kernel); null = all of them
+    const int nmine = wlist ? wcount[5] : R;
+    if (nmine == 0) return;
     const int T = TT ? TT : Trt;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     unsigned char* wbase = smem + LUT_SMEM + wid * WARP_SMEM;         // [2][WARP_BUF] staging, then [2][32] float4 row descriptors
@@ -616,41 +621,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
     if (tid == 0) g_whatif_base = outf;
     __syncthreads();
 #endif
-#ifdef BPC_CTA_ROI
-    // CTA = ROI, warp w = strip w (+ nwarps, ...): the strips of a crop advance together (one CTA barrier per ring slot in the
-    // streaming path), so a whole output row of every plane reaches L2 / DRAM within a short window and neighbouring strips
-    // fetch their overlapping source lines at about the same time.
-    __shared__ int s_roi[2];
-    const int nth = (int)blockDim.x, nwarps = nth >> 5;
-    const int nstrips = (T + 31) >> 5;
-    if (tid == 0) s_roi[0] = atomicAdd(wcount, 1);
-    __syncthreads();
-    for (int it = 0;; ++it) {
-        const int roi = s_roi[it & 1];
-        if (roi >= R) break;
-        int roi_next = 0;
-        if (tid == 0) roi_next = atomicAdd(wcount, 1);          // consumed at the end of this crop: the round trip is hidden
-        const RoiGeom* gp = geom + roi;
-        const int cls = gp->cls;
-        const int new_w = gp->new_w, new_h = gp->new_h, dx0 = gp->dx, dy0 = gp->dy;
-        if (cls == 0) {
-            out.pad_rows(roi, 0, T, tid, nth);
-        } else if (cls == 1 || cls == 3 || cls == 4) {
-            out.pad_rows(roi, 0, dy0, tid, nth);                // whole rows above / below: contiguous runs
-            out.pad_rows(roi, dy0 + new_h, T, tid, nth);
-        }
-        if (cls == 1 || cls == 3 || cls == 4)
-    for (int slot = wid; slot < nstrips; slot += nwarps) {
-        const int nact = min(nwarps, nstrips - (slot - wid));   // warps working in this pass (named-barrier width)
-        const bool touches = slot * 32 < dx0 + new_w && slot * 32 + 32 > dx0;
-        if (!touches && !(ALIGNED && cls == 1)) {
-            const int xp = slot * 32 + lane;                    // a strip beside the resized image: fill
-            if (xp < T)
-                for (int r = 0; r < new_h; ++r) out.pad(roi, dy0 + r, xp);
-            continue;
-        }
-#else
-    const long long nitems = (long long)R * nslot;
+    const long long nitems = (long long)nmine * nslot;
 
     for (;;) {
         int item = 0;
@@ -659,10 +630,11 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
         if (item >= nitems) break;
         // ROI-major order: a ROI's strips and its (store-only) padding item run at about the same time, which keeps
         // whole output rows together in DRAM and blends store-bound with issue-bound work (padding items last: -8 %)
-        const int roi = item / nslot, slot = item - roi * nslot;
+        const int ri = item / nslot, slot = item - ri * nslot;
+        const int roi = wlist ? wlist[R - 1 - ri] : ri;
         const RoiGeom* gp = geom + roi;
         const int cls = gp->cls;
-        if (cls == -1 || cls == 2 || (cls == 1 && skip_cls1)) continue;
+        if (cls == -1 || cls == 2) continue;
         const int new_w = gp->new_w, new_h = gp->new_h, dx0 = gp->dx, dy0 = gp->dy;
 
         if (slot == nslot - 1) {
@@ -680,9 +652,6 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             continue;
         }
         if (cls == 0 || slot * 32 >= dx0 + new_w || slot * 32 + 32 <= dx0) continue;
-        const int nact = 1;
-        const bool touches = true;
-#endif
 
         // ---------------- output columns [32 slot, 32 slot + 32): full 128-byte lines per plane and row ----------------
         const int x = slot * 32 + lane;
@@ -875,27 +844,6 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                     bulk_g2s(dring + 8u * STREAM_ROWS * j, ysrc + 8ull * STREAM_ROWS * c, 8u * STREAM_ROWS, bar_s + 8 * j);
                 }
             };
-#ifdef BPC_CTA_ROI
-            if (!touches) {
-                // a strip beside the resized image keeps pace with its neighbours: per ring slot, the fill value for the output
-                // rows that the slot's source rows complete
-                const float2* yrec = reinterpret_cast<const float2*>(ydesc + (size_t)roi * ystride);
-                float* o = outf + ((size_t)roi * 3 * T + dy0) * T + x;
-                int ydone = 0;
-                for (int c = 0; c < nchunks; ++c) {
-                    asm volatile("bar.sync 1, %0;" :: "r"(nact * 32) : "memory");
-                    const float ba = (lane < STREAM_ROWS) ? yrec[c * STREAM_ROWS + lane].x : 0.f;
-                    const int ndone = __popc(__ballot_sync(0xffffffffu, __float_as_int(ba) < 0));
-                    if (x < T)
-                        for (int r = 0; r < ndone; ++r) {
-                            if (OUT_U8) out.pad(roi, dy0 + ydone + r, x);
-                            else { o[0] = out.padf[0]; o[plane] = out.padf[1]; o[2 * plane] = out.padf[2]; o += T; }
-                        }
-                    ydone += ndone;
-                }
-                continue;
-            }
-#endif
             __syncwarp();                                   // previous item finished with the buffers
             for (int c = 0; c < min(nsl, nchunks); ++c) issue(c, c);
             u64 acc01 = 0ull;
@@ -905,9 +853,6 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             const bool store_ok = (TT && TT % 32 == 0) || x < T;
             int j = 0;
             for (int c = 0; c < nchunks; ++c) {
-#ifdef BPC_CTA_ROI
-                asm volatile("bar.sync 1, %0;" :: "r"(nact * 32) : "memory");
-#endif
                 mbar_wait(bar_s + 8 * j, (ph >> j) & 1u); ph ^= 1u << j;
                 const unsigned rbase = wbase_s + (unsigned)j * slot_bytes + colc4;
 #pragma unroll
@@ -1086,32 +1031,33 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             }
         }
     }
-#ifdef BPC_CTA_ROI
-        if (tid == 0) s_roi[(it + 1) & 1] = roi_next;
-        __syncthreads();
-    }
-#endif
 }
 
 // ------------------------------------------------------------------------------------------------------
-// CTA kernel: class 1 (area, <= 3 taps per axis), one crop per CTA, warp-specialised
+// CTA kernel: classes 1 and 3, one crop per CTA, warp-specialised
 // ------------------------------------------------------------------------------------------------------
-// Warps 0 .. NS-1 (NS = T / 32 strips) are the consumers of bpc_crop_warp_kernel's streaming path: one lane per output column,
-// source rows in order, (ba, bb) records per source row.  What changed is who feeds them: the LAST warp is a producer whose
-// lane 0 walks the class-1 list (atomic counter), and per ring slot issues ONE 2-D tensor copy of eight FULL-WIDTH source
-// rows of the crop plus the 64 bytes of their records -- seven times fewer TMA operations than one box per strip, every
-// source byte fetched once per crop, and the ~300-cycle scoreboard wait behind each TMA issue (measured: 13 % of the old
-// kernel's warp time) sits in a warp that has nothing else to do.  The producer runs ahead across crops (ring of four slots,
-// header ring of two crops), which also hides the per-crop set-up round trips.  Consumers meet on the slots' full / empty
-// mbarriers, so the strips of one crop stay within four slots of each other: whole 896-byte output rows of a plane reach L2
-// close together, and the rows above / below the resized image are written as contiguous runs by all consumer threads.
+// Warps 0 .. NS-1 (NS = T / 32 strips) are consumers: one lane per output column, source rows in order.  The LAST warp is a
+// producer whose lane 0 walks the list of class-1 / class-3 crops (atomic counter) and, per crop, copies the crop's block of
+// row descriptors into shared memory (one bulk copy) and then, per ring slot, issues ONE 2-D tensor copy of eight FULL-WIDTH
+// source rows -- seven times fewer TMA operations than one box per strip, every source byte fetched once per crop, and the
+// ~300-cycle scoreboard wait behind each TMA issue (measured: 13 % of the per-strip kernel's warp time) sits in a warp that has
+// nothing else to do.  The producer runs ahead across crops (ring of four slots, two descriptor blocks), which also hides
+// the per-crop set-up round trips.  Consumers meet on the slots' full / empty mbarriers, so the strips of one crop stay within
+// four slots of each other: whole 896-byte output rows of a plane reach L2 close together, and the rows above / below the
+// resized image are written as contiguous runs by all consumer threads.
+//   class 1 (area, <= 3 taps): per SOURCE row a (ba, bb) record (see bpc_crop_prep_kernel); a row whose ba has the sign bit
+//            set closes the open output row (LUT, three 128-byte stores) and opens the next with weight bb;
+//   class 3 (fixed-point bilinear, the box grows): per OUTPUT row (b0, b1, second source row, first source row); an output row
+//            is emitted as soon as the slot holding its second source row has landed -- its first row is the previous output
+//            row's first or second row, whose horizontal pass is still in registers.
 constexpr int CTA_ROWS = 8;                  // source rows per ring slot (= one TMA box)
 constexpr int CTA_NSLOT = 4;
 constexpr int CTA_NMAPS = 25;                // box widths 64, 128, ... 1600 bytes (8-byte elements)
 constexpr int CTA_MAX_T = 256;               // 8 consumer warps
 struct CtaMaps { CUtensorMap m[CTA_NMAPS]; };
 __host__ __device__ __forceinline__ int cta_pitch_max(int T) { return ((15 + 3 * (2 * T - 1) + 12 + 63) >> 6) << 6; }
-__host__ __device__ __forceinline__ int cta_smem_bytes(int T) { return LUT_SMEM + CTA_NSLOT * CTA_ROWS * cta_pitch_max(T) + CTA_NSLOT * 8 * CTA_ROWS + 256; }
+__host__ __device__ __forceinline__ int cta_desc_bytes(int T) { return (desc_stride(T) + 8) * 16; }
+__host__ __device__ __forceinline__ int cta_smem_bytes(int T) { return LUT_SMEM + CTA_NSLOT * CTA_ROWS * cta_pitch_max(T) + 2 * cta_desc_bytes(T) + 256; }
 
 __device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
 
@@ -1127,10 +1073,11 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int NS = (T + 31) >> 5;                                   // consumer warps; warp NS is the producer
     const int slot_bytes = CTA_ROWS * cta_pitch_max(T);
+    const int desc_bytes = cta_desc_bytes(T);
     const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
     const unsigned ring_s = smem_s + LUT_SMEM;
-    const unsigned rec_s = ring_s + CTA_NSLOT * slot_bytes;        // [CTA_NSLOT][CTA_ROWS] float2
-    const unsigned misc_s = rec_s + CTA_NSLOT * 8 * CTA_ROWS;
+    const unsigned desc_s = ring_s + CTA_NSLOT * slot_bytes;       // [2][ystride] float4: the current and the next crop's row descriptors
+    const unsigned misc_s = desc_s + 2 * desc_bytes;
     const unsigned full_s = misc_s, empty_s = misc_s + 8 * CTA_NSLOT, hfull_s = misc_s + 16 * CTA_NSLOT, hempty_s = hfull_s + 16;
     volatile int* hdr = reinterpret_cast<volatile int*>(smem + (misc_s - smem_s) + 16 * CTA_NSLOT + 32);       // [2] crop index
     if (tid == 0) {
@@ -1170,22 +1117,21 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
             const unsigned long long src = gp->src;
             const int w = gp->w, h = gp->h;
             hdr[hb] = roi;
-            mbar_arrive(hfull_s + 8 * hb);
+            mbar_expect_tx(hfull_s + 8 * hb, (unsigned)desc_bytes);
+            bulk_g2s(desc_s + hb * desc_bytes, (unsigned long long)(uintptr_t)(ydesc + (size_t)roi * ystride), (unsigned)desc_bytes, hfull_s + 8 * hb);
             const int mis0 = (int)(src & 15ull);
             const int pitch = ((mis0 + 3 * w + 12 + 63) >> 6) << 6;
             const unsigned long long off = (src & ~15ull) - (unsigned long long)(uintptr_t)images;
             const int row0 = (int)(off / rowstride);
             const int x8 = (int)((off - (unsigned long long)row0 * rowstride) >> 3);
             const CUtensorMap* map = &tm.m[(pitch >> 6) - 1];
-            const unsigned long long yrec = (unsigned long long)(uintptr_t)(ydesc + (size_t)roi * ystride);
             const int nchunks = (h + CTA_ROWS - 1) / CTA_ROWS;
             for (int c = 0; c < nchunks; ++c, ++cg) {
                 const unsigned j = cg % CTA_NSLOT;
                 if (cg >= CTA_NSLOT) mbar_wait(empty_s + 8 * j, ((cg / CTA_NSLOT) - 1) & 1);
-                mbar_expect_tx(full_s + 8 * j, (unsigned)(CTA_ROWS * pitch + 8 * CTA_ROWS));
+                mbar_expect_tx(full_s + 8 * j, (unsigned)(CTA_ROWS * pitch));
                 asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                              :: "r"(ring_s + j * slot_bytes), "l"(map), "r"(x8), "r"(row0 + c * CTA_ROWS), "r"(full_s + 8 * j) : "memory");
-                bulk_g2s(rec_s + 8u * CTA_ROWS * j, yrec + 8ull * CTA_ROWS * c, 8u * CTA_ROWS, full_s + 8 * j);
             }
             idx = idx_next;
         }
@@ -1204,14 +1150,14 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
         const int hb = hi & 1;
         mbar_wait(hfull_s + 8 * hb, (hi >> 1) & 1);
         const int roi = hdr[hb];
-        __syncwarp();
-        if (lane == 0) mbar_arrive(hempty_s + 8 * hb);
         if (roi < 0) break;
         const RoiGeom* gp = geom + roi;
+        const int cls = gp->cls;
         const int new_w = gp->new_w, new_h = gp->new_h, dx0 = gp->dx, dy0 = gp->dy, h = gp->h;
         const int mis0 = (int)(gp->src & 15ull);
         const int pitch = ((mis0 + 3 * gp->w + 12 + 63) >> 6) << 6;
         const int nchunks = (h + CTA_ROWS - 1) / CTA_ROWS;
+        const unsigned dsc = desc_s + hb * desc_bytes;
         out.pad_rows(roi, 0, dy0, tid, nthc);                       // whole rows above / below: contiguous runs
         out.pad_rows(roi, dy0 + new_h, T, tid, nthc);
         const int xr = x - dx0;
@@ -1225,10 +1171,24 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
             for (int c = 0; c < nchunks; ++c, ++cg) {
                 const unsigned j = cg % CTA_NSLOT;
                 mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
-                const float ba = (lane < CTA_ROWS) ? lds_f32(rec_s + 8u * CTA_ROWS * j + 8u * lane) : 0.f;
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty_s + 8 * j);
-                const int ndone = __popc(__ballot_sync(0xffffffffu, __float_as_int(ba) < 0));
+                int ndone;
+                if (cls == 1) {
+                    const float ba = (lane < CTA_ROWS) ? lds_f32(dsc + 8u * (unsigned)(c * CTA_ROWS + lane)) : 0.f;
+                    ndone = __popc(__ballot_sync(0xffffffffu, __float_as_int(ba) < 0));
+                } else {
+                    // output rows whose second source row lies in this slot (monotone in y)
+                    const int last_row = c * CTA_ROWS + CTA_ROWS - 1;
+                    ndone = 0;
+                    for (int y0 = ydone; y0 < new_h; y0 += 32) {
+                        const int yy = y0 + lane;
+                        const bool ok = yy < new_h && __float_as_int(lds_f4(dsc + 16u * (unsigned)min(yy, new_h - 1)).z) <= last_row;
+                        const int n = __popc(__ballot_sync(0xffffffffu, ok));
+                        ndone += n;
+                        if (n < 32) break;
+                    }
+                }
                 if (store_ok)
                     for (int r = 0; r < ndone; ++r) {
                         if (OUT_U8) out.pad(roi, dy0 + ydone + r, x);
@@ -1236,6 +1196,8 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
                     }
                 ydone += ndone;
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(hempty_s + 8 * hb);         // done with this crop's descriptor block
             continue;
         }
         const float4 xd = xdesc[(size_t)roi * ds + min(max(xr, 0), new_w - 1)];
@@ -1243,60 +1205,115 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
         const int colc = 3 * xs + mis0;
         const unsigned colc4 = (unsigned)(colc & ~3);
         const int shc = (colc & 3) * 8;
-        ColW cw;
-        cw.set(xd.x, xd.y, xd.z);
-        if (!active) {                               // beside the image: every row sums to 256 -> LUT entry 256 = fill
-            cw.w[0] = cw.w[1] = cw.w[2] = 0.f;
-            cw.c[0] = 256.f; cw.c[1] = cw.c[2] = 0.f;
-        }
-        u64 acc01 = 0ull;
-        float acc2 = 0.f;
-        unsigned roff = 0;                                // element offset of the open output row from optr
-        int yout = 0;
-        for (int c = 0; c < nchunks; ++c, ++cg) {
-            const unsigned j = cg % CTA_NSLOT;
-            mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
-            const unsigned rbase = ring_s + j * slot_bytes + colc4;
+        if (cls == 1) {
+            ColW cw;
+            cw.set(xd.x, xd.y, xd.z);
+            if (!active) {                               // beside the image: every row sums to 256 -> LUT entry 256 = fill
+                cw.w[0] = cw.w[1] = cw.w[2] = 0.f;
+                cw.c[0] = 256.f; cw.c[1] = cw.c[2] = 0.f;
+            }
+            u64 acc01 = 0ull;
+            float acc2 = 0.f;
+            unsigned roff = 0;                                // element offset of the open output row from optr
+            int yout = 0;
+            for (int c = 0; c < nchunks; ++c, ++cg) {
+                const unsigned j = cg % CTA_NSLOT;
+                mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
+                const unsigned rbase = ring_s + j * slot_bytes + colc4;
+                const unsigned rec = dsc + 8u * CTA_ROWS * (unsigned)c;
 #pragma unroll
-            for (int half = 0; half < CTA_ROWS / 4; ++half) {
-                const float4 dA = lds_f4(rec_s + 8u * CTA_ROWS * j + 32u * half), dB = lds_f4(rec_s + 8u * CTA_ROWS * j + 32u * half + 16);
-                u64 h01[4];
-                float h2[4];
+                for (int half = 0; half < CTA_ROWS / 4; ++half) {
+                    const float4 dA = lds_f4(rec + 32u * half), dB = lds_f4(rec + 32u * half + 16);
+                    u64 h01[4];
+                    float h2[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) h_area3(rbase + (unsigned)((4 * half + k) * pitch), shc, cw, h01[k], h2[k]);
-                if (half == CTA_ROWS / 4 - 1) {
-                    __syncwarp();                           // every lane has read slot j
-                    if (lane == 0) mbar_arrive(empty_s + 8 * j);
-                }
-                const float ba[4] = {dA.x, dA.z, dB.x, dB.z}, bb[4] = {dA.y, dA.w, dB.y, dB.w};
+                    for (int k = 0; k < 4; ++k) h_area3(rbase + (unsigned)((4 * half + k) * pitch), shc, cw, h01[k], h2[k]);
+                    if (half == CTA_ROWS / 4 - 1) {
+                        __syncwarp();                           // every lane has read slot j
+                        if (lane == 0) mbar_arrive(empty_s + 8 * j);
+                    }
+                    const float ba[4] = {dA.x, dA.z, dB.x, dB.z}, bb[4] = {dA.y, dA.w, dB.y, dB.w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float wa = fabsf(ba[k]);
-                    acc01 = fadd2(acc01, fprod2(pack2(wa, wa), h01[k], nz2));
-                    acc2 = __fadd_rn(acc2, __fmul_rn(wa, h2[k]));
-                    if (__float_as_int(ba[k]) < 0) {            // output row complete
-                        float a0f, a1f;
-                        unpack2(acc01, a0f, a1f);
-                        if (OUT_U8) {
-                            if (active) out.px(roi, dy0 + yout, x, round_u8(a0f), round_u8(a1f), round_u8(acc2));
-                            else if (x < T) out.pad(roi, dy0 + yout, x);
-                            ++yout;
-                        } else {
-                            const unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
-                            if (store_ok) {
-                                float* o = optr + roff;
-                                stg_out<0>(o, lds_f32(swap ? l2 : l0));
-                                stg_out<1>(o + plane, lds_f32(l1 + 4 * LUT_STRIDE));
-                                stg_out<2>(o + 2 * plane, lds_f32((swap ? l0 : l2) + 8 * LUT_STRIDE));
+                    for (int k = 0; k < 4; ++k) {
+                        const float wa = fabsf(ba[k]);
+                        acc01 = fadd2(acc01, fprod2(pack2(wa, wa), h01[k], nz2));
+                        acc2 = __fadd_rn(acc2, __fmul_rn(wa, h2[k]));
+                        if (__float_as_int(ba[k]) < 0) {            // output row complete
+                            float a0f, a1f;
+                            unpack2(acc01, a0f, a1f);
+                            if (OUT_U8) {
+                                if (active) out.px(roi, dy0 + yout, x, round_u8(a0f), round_u8(a1f), round_u8(acc2));
+                                else if (x < T) out.pad(roi, dy0 + yout, x);
+                                ++yout;
+                            } else {
+                                const unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
+                                if (store_ok) {
+                                    float* o = optr + roff;
+                                    stg_out<0>(o, lds_f32(swap ? l2 : l0));
+                                    stg_out<1>(o + plane, lds_f32(l1 + 4 * LUT_STRIDE));
+                                    stg_out<2>(o + 2 * plane, lds_f32((swap ? l0 : l2) + 8 * LUT_STRIDE));
+                                }
+                                roff += (unsigned)T;
                             }
-                            roff += (unsigned)T;
+                            acc01 = fprod2(pack2(bb[k], bb[k]), h01[k], nz2);
+                            acc2 = __fmul_rn(bb[k], h2[k]);
                         }
-                        acc01 = fprod2(pack2(bb[k], bb[k]), h01[k], nz2);
-                        acc2 = __fmul_rn(bb[k], h2[k]);
                     }
                 }
             }
+        } else {
+            // ---------------- class 3: fixed-point bilinear ----------------
+            const int xw0 = __float_as_int(xd.x), xw1 = __float_as_int(xd.y);
+            const unsigned lut_s = smem_s;
+            int rowA = -1, rowB = -1;
+            int HA[3] = {0, 0, 0}, HB[3] = {0, 0, 0};
+            int y = 0;
+            float4 d = lds_f4(dsc);
+            for (int c = 0; c < nchunks; ++c, ++cg) {
+                const unsigned j = cg % CTA_NSLOT;
+                mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
+                const int last_row = c * CTA_ROWS + CTA_ROWS - 1;
+                const unsigned sbase = ring_s + j * slot_bytes + colc4 - (unsigned)(c * CTA_ROWS * pitch);     // source row r at sbase + r * pitch
+                while (y < new_h) {
+                    // (b * H) >> 16 as the high word of (b << 16) * H: one IMAD.HI instead of a multiply and a shift (0 <= b <= 2048, 0 <= H < 2^15)
+                    const unsigned b0 = (unsigned)__float_as_int(d.x) << 16, b1 = (unsigned)__float_as_int(d.y) << 16;
+                    const int sy0 = __float_as_int(d.w), sy1 = __float_as_int(d.z);
+                    if (sy1 > last_row) break;
+                    ++y;
+                    d = lds_f4(dsc + 16u * (unsigned)y);              // next row's descriptor behind this row's arithmetic
+                    if (active) {
+                        if (sy0 != rowA) {
+                            if (sy0 == rowB) { HA[0] = HB[0]; HA[1] = HB[1]; HA[2] = HB[2]; }
+                            else h_lin(sbase + (unsigned)(sy0 * pitch), shc, xw0, xw1, HA);
+                            rowA = sy0;
+                        }
+                        if (sy1 != rowB) {
+                            if (sy1 == rowA) { HB[0] = HA[0]; HB[1] = HA[1]; HB[2] = HA[2]; }
+                            else h_lin(sbase + (unsigned)(sy1 * pitch), shc, xw0, xw1, HB);
+                            rowB = sy1;
+                        }
+                        unsigned o[3];                      // 4 * value + 2 low bits
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) o[k] = __umulhi(b1, (unsigned)HB[k]) + (__umulhi(b0, (unsigned)HA[k]) + 2u);
+                        if (OUT_U8) {
+                            out.px(roi, dy0 + y - 1, x, (int)(o[0] >> 2) & 255, (int)(o[1] >> 2) & 255, (int)(o[2] >> 2) & 255);
+                        } else {
+                            stg_out<0>(optr, lds_f32(lut_s + ((swap ? o[2] : o[0]) & 0x3fcu)));
+                            stg_out<1>(optr + plane, lds_f32(lut_s + 4 * LUT_STRIDE + (o[1] & 0x3fcu)));
+                            stg_out<2>(optr + 2 * plane, lds_f32(lut_s + 8 * LUT_STRIDE + ((swap ? o[0] : o[2]) & 0x3fcu)));
+                            optr += T;
+                        }
+                    } else if (x < T) {
+                        if (OUT_U8) out.pad(roi, dy0 + y - 1, x);
+                        else { optr[0] = out.padf[0]; optr[plane] = out.padf[1]; optr[2 * plane] = out.padf[2]; optr += T; }
+                    }
+                }
+                __syncwarp();                               // every lane is done with slot j
+                if (lane == 0) mbar_arrive(empty_s + 8 * j);
+            }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(hempty_s + 8 * hb);             // done with this crop's descriptor block
     }
 }
 
@@ -1662,7 +1679,7 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
     }
     {
         typedef void (*WarpFn)(const uint8_t*, int, int, int, const RoiGeom*, const float4*, const float4*, int32_t*, int, int, int,
-                               uchar4, int, const float*, float*, uint8_t*, const TmapSet);
+                               uchar4, int, const float*, float*, uint8_t*, const TmapSet, const int32_t*);
         TmapSet tmaps;
         const int terr = tensor_maps(images, B, H, W, aligned, &tmaps);
         if (terr != BPC_OK) return terr;
@@ -1679,22 +1696,16 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
         // the same constant on every call: idempotent, so concurrent callers cannot interleave set(small) / launch(large)
         e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, WARPK_SMEM);
         if (e != cudaSuccess) return (int)e;
-#ifdef BPC_CTA_ROI
-        const int nstrips = (T + 31) / 32;
-        const int cta_threads = 32 * (nstrips < WARPK_WARPS ? nstrips : WARPK_WARPS);
-        const long long want = R;
-#else
         const int cta_threads = 256;
         const long long nitems = (long long)R * nslot;
         const long long want = (nitems + WARPK_WARPS - 1) / WARPK_WARPS;
-#endif
         int dev = 0, sms = 148, per_sm = 3;                     // persistent grid: every resident CTA slot, no more
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, cta_threads, WARPK_SMEM) != cudaSuccess || per_sm < 1) per_sm = 1;
         const long long slots = (long long)sms * per_sm;
         const int grid = (int)(want < slots ? want : slots);
-        fn<<<grid, cta_threads, WARPK_SMEM, st>>>(images, B, H, W, geom, xdesc, ydesc, wcount, R, T, nslot, f4, (swap_rb ? 1 : 0) | (use_cta ? 0x100 : 0), lut, outf, outb, tmaps);
+        fn<<<grid, cta_threads, WARPK_SMEM, st>>>(images, B, H, W, geom, xdesc, ydesc, wcount, R, T, nslot, f4, swap_rb, lut, outf, outb, tmaps, use_cta ? list1 : nullptr);
         BPC_LAUNCH_CHECK();
     }
     const int nbands = (T + CROP_BAND - 1) / CROP_BAND;
