@@ -55,6 +55,12 @@ static_assert(LUT_SMEM % 128 == 0 && LUT_SMEM >= 3 * LUT_STRIDE * 4, "LUT block"
 // descriptors per ROI: x axis ds float4, y axis ds + 8 float4 (class 1 reads the y block as 2*ds + 16 float2 source-row records),
 // ds = T rounded up to 32
 __host__ __device__ __forceinline__ int desc_stride(int T) { return (T + 31) & ~31; }
+// float4 records per ROI on the y axis: ds + 8 (class 1 reads the block as 2 ds + 16 float2 source-row records); up to T = 256 the
+// block also holds the source-row records of a class-4 crop for the CTA kernel (h <= 5 T rows + one padded slot + 16)
+__host__ __device__ __forceinline__ int ydesc_stride(int T) {
+    const int base = desc_stride(T) + 8, rows4 = (5 * T + 32 + 1) / 2;
+    return (T <= 256 && rows4 > base) ? rows4 : base;
+}
 
 struct RoiGeom {                             // 88 bytes, workspace
     double scale_x, scale_y, inv_x, inv_y;
@@ -159,6 +165,34 @@ __device__ __forceinline__ void linear_coef(int d, double scale, double inv, int
 }
 
 
+// Per-SOURCE-row records of an area resize with at most `maxtaps` taps per output row (collective over the 256 threads of a prep
+// CTA): record s = (ba, bb); |ba| = weight of source row s in the output row being accumulated, sign bit of ba set = that output
+// row is complete after row s; bb = weight of row s as the first tap of the next output row (+0 if it has none there).  Rows
+// [h, hpad) stay zero (no contribution, no completed row) so that whole ring slots run to completion.  *bad is set when the taps
+// do not have this shape (then the ROI takes the generic path).
+__device__ void src_row_records(float2* ysrc, int cap, const RoiGeom& g, int maxtaps, int tid, int* bad) {
+    const int hpad = min(cap, ((g.h + STREAM_ROWS - 1) / STREAM_ROWS) * STREAM_ROWS + STREAM_ROWS);
+    if (g.h + STREAM_ROWS > cap) *bad = 1;
+    for (int s = tid; s < hpad; s += 256) ysrc[s] = make_float2(0.f, 0.f);
+    __syncthreads();
+    for (int d = tid; d < g.new_h && !*bad; d += 256) {
+        int ys, yn, fl, pys = 0, pyn = 0, pfl; float bf, bm, bl, pf, pm, pl;
+        area_taps(d, g.scale_y, g.h, ys, yn, bf, bm, bl, fl);
+        if (d > 0) area_taps(d - 1, g.scale_y, g.h, pys, pyn, pf, pm, pl, pfl);
+        const int prev_last = d > 0 ? pys + pyn - 1 : -1;
+        if (yn < 1 || yn > maxtaps || ys < prev_last || ys + yn > g.h) { *bad = 1; break; }
+        for (int t = 0; t < yn; ++t) {
+            const int s = ys + t;
+            const bool shared_first = (t == 0 && s == prev_last);       // row s also closes output row d - 1
+            if (shared_first && yn == 1) { *bad = 1; break; }           // one source row closing two output rows: generic path
+            float wv = (t == 0 && (fl & 1)) ? bf : ((t == yn - 1 && (fl & 2)) ? bl : bm);
+            if (t == yn - 1) wv = __int_as_float(__float_as_int(wv) | (int)0x80000000u);
+            if (shared_first) ysrc[s].y = wv; else ysrc[s].x = wv;
+        }
+    }
+    __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------------------
 // prep: geometry, classification and tap descriptors, one CTA per ROI
 // ------------------------------------------------------------------------------------------------------
@@ -226,7 +260,8 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                         const int seg_px = (int)(31.0 * g.scale_x) + (int)ceil(g.scale_x) + 3;
                         const int pitch_max = ((3 * seg_px + 46) >> 4) << 4;
                         const bool taps6 = (int)ceil(g.scale_x) + 1 <= 6 && (int)ceil(g.scale_y) + 1 <= 6;
-                        g.cls = (taps6 && pitch_max <= TMAP_MAX_PITCH) ? 4 : 2;        // four ring slots of >= 2 rows fit 2 * WARP_BUF
+                        // per-strip kernel: four ring slots of >= 2 rows fit 2 * WARP_BUF; CTA kernel (full-width rows): any width
+                        g.cls = (taps6 && ((stream_ok & 2) || pitch_max <= TMAP_MAX_PITCH)) ? 4 : 2;
                     } else g.cls = 2;
                 }
             }
@@ -236,10 +271,10 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
     __syncthreads();
     const int cls = g.cls;
     float4* xd = xdesc + (size_t)roi * ds;
-    float4* yd = ydesc + (size_t)roi * (ds + 8);
+    float4* yd = ydesc + (size_t)roi * ydesc_stride(T);
     if (cls == 4) {
         // (w_first, w_middle, w_last, bits(start | taps << 24)); a missing first / last tap takes the middle weight
-        for (int axis = 0; axis < 2; ++axis) {
+        for (int axis = 0; axis < ((stream_ok & 2) ? 1 : 2); ++axis) {
             const int nd = axis ? g.new_h : g.new_w;
             for (int d = tid; d < nd; d += 256) {
                 int st, n, flags; float af, am, al;
@@ -249,41 +284,24 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
                 (axis ? yd : xd)[d] = make_float4(w0, am, wl, __int_as_float(st | (n << 24)));
             }
         }
+        if (stream_ok & 2) {
+            src_row_records(reinterpret_cast<float2*>(yd), 2 * ydesc_stride(T), g, 6, tid, &s_bad);
+            if (s_bad && tid == 0) { g.cls = 2; }
+        }
     } else if (cls == 1) {
         for (int d = tid; d < g.new_w; d += 256) {
             int xs, xn; float w0, w1, w2;
             area_taps3(d, g.scale_x, g.w, xs, xn, w0, w1, w2);
             xd[d] = make_float4(w0, w1, w2, __int_as_float(xs));
         }
-        if (!stream_ok) {
+        if (!(stream_ok & 1)) {
             for (int d = tid; d < g.new_h; d += 256) {
                 int ys, yn; float b0, b1, b2;
                 area_taps3(d, g.scale_y, g.h, ys, yn, b0, b1, b2);
                 yd[d] = make_float4(b0, b1, b2, __int_as_float(ys | (yn << 24)));
             }
         } else {
-            // per-source-row records; rows [h, hpad) stay zero (no contribution, no completed row)
-            float2* ysrc = reinterpret_cast<float2*>(yd);
-            const int hpad = min(2 * ds + YSRC_PAD, ((g.h + STREAM_ROWS - 1) / STREAM_ROWS) * STREAM_ROWS + STREAM_ROWS);
-            if (g.h + STREAM_ROWS > 2 * ds + YSRC_PAD) s_bad = 1;            // cannot happen for scale_y < 2 (h < 2 T)
-            for (int s = tid; s < hpad; s += 256) ysrc[s] = make_float2(0.f, 0.f);
-            __syncthreads();
-            for (int d = tid; d < g.new_h && !s_bad; d += 256) {
-                int ys, yn, pys = 0, pyn = 0; float b[3], pb[3];
-                area_taps3(d, g.scale_y, g.h, ys, yn, b[0], b[1], b[2]);
-                if (d > 0) area_taps3(d - 1, g.scale_y, g.h, pys, pyn, pb[0], pb[1], pb[2]);
-                const int prev_last = d > 0 ? pys + pyn - 1 : -1;
-                if (yn < 1 || yn > 3 || ys < prev_last || ys + yn > g.h) { s_bad = 1; break; }
-                for (int t = 0; t < yn; ++t) {
-                    const int s = ys + t;
-                    const bool shared_first = (t == 0 && s == prev_last);       // row s also closes output row d - 1
-                    if (shared_first && yn == 1) { s_bad = 1; break; }          // one source row closing two output rows: generic path
-                    float wv = b[t];
-                    if (t == yn - 1) wv = __int_as_float(__float_as_int(wv) | (int)0x80000000u);
-                    if (shared_first) ysrc[s].y = wv; else ysrc[s].x = wv;
-                }
-            }
-            __syncthreads();
+            src_row_records(reinterpret_cast<float2*>(yd), 2 * ds + YSRC_PAD, g, 3, tid, &s_bad);
             if (s_bad && tid == 0) { g.cls = 2; }
         }
     } else if (cls == 3) {
@@ -305,8 +323,8 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
         if (g.cls == 2) glist[atomicAdd(gcount, 1)] = roi;
         if (list1 != nullptr) {
             // crops streamed by bpc_crop_cta_kernel from the front of the list, those of bpc_crop_warp_kernel from its back
-            if (g.cls == 1 || g.cls == 3) list1[atomicAdd(gcount + 8, 1)] = roi;
-            else if (g.cls == 0 || g.cls == 4) list1[R - 1 - atomicAdd(gcount + 9, 1)] = roi;
+            if (g.cls == 1 || g.cls == 3 || g.cls == 4) list1[atomicAdd(gcount + 8, 1)] = roi;
+            else if (g.cls == 0) list1[R - 1 - atomicAdd(gcount + 9, 1)] = roi;
         }
         geom[roi] = g;
     }
@@ -610,7 +628,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
     if (!OUT_U8 && tid < 3) lut[tid * LUT_STRIDE + 256] = out.padf[tid];  // entry 256 = fill: what a lane beside the image looks up
     __syncthreads();
     const unsigned lut_m = *reinterpret_cast<volatile unsigned*>(smem + 3 * LUT_STRIDE * 4);
-    const int ds = desc_stride(T), ystride = ds + 8;
+    const int ds = desc_stride(T), ystride = ydesc_stride(T);
     constexpr bool swap = SWAP;
     const size_t plane = (size_t)T * T;
     const unsigned long long rowstride = (unsigned long long)W * 3ull;
@@ -1034,7 +1052,7 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
 }
 
 // ------------------------------------------------------------------------------------------------------
-// CTA kernel: classes 1 and 3, one crop per CTA, warp-specialised
+// CTA kernel: classes 1, 3 and 4, one crop per CTA, warp-specialised
 // ------------------------------------------------------------------------------------------------------
 // Warps 0 .. NS-1 (NS = T / 32 strips) are consumers: one lane per output column, source rows in order.  The LAST warp is a
 // producer whose lane 0 walks the list of class-1 / class-3 crops (atomic counter) and, per crop, copies the crop's block of
@@ -1056,7 +1074,10 @@ constexpr int CTA_NMAPS = 25;                // box widths 64, 128, ... 1600 byt
 constexpr int CTA_MAX_T = 256;               // 8 consumer warps
 struct CtaMaps { CUtensorMap m[CTA_NMAPS]; };
 __host__ __device__ __forceinline__ int cta_pitch_max(int T) { return ((15 + 3 * (2 * T - 1) + 12 + 63) >> 6) << 6; }
-__host__ __device__ __forceinline__ int cta_desc_bytes(int T) { return (desc_stride(T) + 8) * 16; }
+// staged bytes per source row of a crop: misalignment of its first byte + 3 w + what the widest horizontal pass over-reads
+// (class 1: three words from the aligned tap address; class 4: up to six taps padded to the warp maximum)
+__host__ __device__ __forceinline__ int cta_pitch(int mis0, int w, int cls) { return ((mis0 + 3 * w + (cls == 4 ? 40 : 12) + 63) >> 6) << 6; }
+__host__ __device__ __forceinline__ int cta_desc_bytes(int T) { return ydesc_stride(T) * 16; }
 __host__ __device__ __forceinline__ int cta_smem_bytes(int T) { return LUT_SMEM + CTA_NSLOT * CTA_ROWS * cta_pitch_max(T) + 2 * cta_desc_bytes(T) + 256; }
 
 __device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
@@ -1072,7 +1093,8 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
     const int T = TT ? TT : Trt;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int NS = (T + 31) >> 5;                                   // consumer warps; warp NS is the producer
-    const int slot_bytes = CTA_ROWS * cta_pitch_max(T);
+    const int pitch_max = cta_pitch_max(T);
+    const int slot_bytes = CTA_ROWS * pitch_max;
     const int desc_bytes = cta_desc_bytes(T);
     const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
     const unsigned ring_s = smem_s + LUT_SMEM;
@@ -1093,8 +1115,9 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
     if (!OUT_U8 && tid < 3) lut[tid * LUT_STRIDE + 256] = out.padf[tid];
     __syncthreads();
     const unsigned lut_m = *reinterpret_cast<volatile unsigned*>(smem + 3 * LUT_STRIDE * 4);
-    const int ds = desc_stride(T), ystride = ds + 8;
+    const int ds = desc_stride(T), ystride = ydesc_stride(T);
     const unsigned long long rowstride = (unsigned long long)W * 3ull;
+    const unsigned long long img_end = (unsigned long long)(uintptr_t)images + (unsigned long long)B * H * rowstride;
     const int n1 = counters[8];
     int32_t* work = counters + 12;
 
@@ -1117,21 +1140,48 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
             const unsigned long long src = gp->src;
             const int w = gp->w, h = gp->h;
             hdr[hb] = roi;
-            mbar_expect_tx(hfull_s + 8 * hb, (unsigned)desc_bytes);
-            bulk_g2s(desc_s + hb * desc_bytes, (unsigned long long)(uintptr_t)(ydesc + (size_t)roi * ystride), (unsigned)desc_bytes, hfull_s + 8 * hb);
+            // the part of the crop's row-descriptor block that will be read: per output row (class 3) or per source row, padded slot included
+            const unsigned dbytes = (unsigned)min(desc_bytes, gp->cls == 3 ? 16 * (gp->new_h + 1) : 8 * (((h + CTA_ROWS - 1) & ~(CTA_ROWS - 1)) + CTA_ROWS));
+            mbar_expect_tx(hfull_s + 8 * hb, dbytes);
+            bulk_g2s(desc_s + hb * desc_bytes, (unsigned long long)(uintptr_t)(ydesc + (size_t)roi * ystride), dbytes, hfull_s + 8 * hb);
             const int mis0 = (int)(src & 15ull);
-            const int pitch = ((mis0 + 3 * w + 12 + 63) >> 6) << 6;
+            const int pitch = cta_pitch(mis0, w, gp->cls);
             const unsigned long long off = (src & ~15ull) - (unsigned long long)(uintptr_t)images;
             const int row0 = (int)(off / rowstride);
             const int x8 = (int)((off - (unsigned long long)row0 * rowstride) >> 3);
-            const CUtensorMap* map = &tm.m[(pitch >> 6) - 1];
-            const int nchunks = (h + CTA_ROWS - 1) / CTA_ROWS;
-            for (int c = 0; c < nchunks; ++c, ++cg) {
-                const unsigned j = cg % CTA_NSLOT;
-                if (cg >= CTA_NSLOT) mbar_wait(empty_s + 8 * j, ((cg / CTA_NSLOT) - 1) & 1);
-                mbar_expect_tx(full_s + 8 * j, (unsigned)(CTA_ROWS * pitch));
-                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                             :: "r"(ring_s + j * slot_bytes), "l"(map), "r"(x8), "r"(row0 + c * CTA_ROWS), "r"(full_s + 8 * j) : "memory");
+            if (pitch <= pitch_max) {
+                // one 2-D tensor copy of eight full-width rows per slot (rows / columns beyond the pool are zero-filled)
+                const CUtensorMap* map = &tm.m[(pitch >> 6) - 1];
+                const int nchunks = (h + CTA_ROWS - 1) / CTA_ROWS;
+                for (int c = 0; c < nchunks; ++c, ++cg) {
+                    const unsigned j = cg % CTA_NSLOT;
+                    if (cg >= CTA_NSLOT) mbar_wait(empty_s + 8 * j, ((cg / CTA_NSLOT) - 1) & 1);
+                    mbar_expect_tx(full_s + 8 * j, (unsigned)(CTA_ROWS * pitch));
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 :: "r"(ring_s + j * slot_bytes), "l"(map), "r"(x8), "r"(row0 + c * CTA_ROWS), "r"(full_s + 8 * j) : "memory");
+                }
+            } else {
+                // wide class-4 crops (rows of up to 5 T pixels): rps rows per slot, one 1-D bulk copy each, clipped to the pool
+                const int rps = slot_bytes / pitch;
+                const int nchunks = (h + rps - 1) / rps;
+                const unsigned long long a0 = src & ~15ull;
+                for (int c = 0; c < nchunks; ++c, ++cg) {
+                    const unsigned j = cg % CTA_NSLOT;
+                    if (cg >= CTA_NSLOT) mbar_wait(empty_s + 8 * j, ((cg / CTA_NSLOT) - 1) & 1);
+                    unsigned total = 0;
+                    for (int r = 0; r < rps; ++r) {
+                        const unsigned long long a = a0 + (unsigned long long)(c * rps + r) * rowstride;
+                        if (a < img_end) total += (unsigned)min((unsigned long long)pitch, (img_end - a) & ~15ull);
+                    }
+                    mbar_expect_tx(full_s + 8 * j, total);
+                    for (int r = 0; r < rps; ++r) {
+                        const unsigned long long a = a0 + (unsigned long long)(c * rps + r) * rowstride;
+                        if (a < img_end) {
+                            const unsigned nb = (unsigned)min((unsigned long long)pitch, (img_end - a) & ~15ull);
+                            if (nb) bulk_g2s(ring_s + j * slot_bytes + (unsigned)(r * pitch), a, nb, full_s + 8 * j);
+                        }
+                    }
+                }
             }
             idx = idx_next;
         }
@@ -1155,8 +1205,9 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
         const int cls = gp->cls;
         const int new_w = gp->new_w, new_h = gp->new_h, dx0 = gp->dx, dy0 = gp->dy, h = gp->h;
         const int mis0 = (int)(gp->src & 15ull);
-        const int pitch = ((mis0 + 3 * gp->w + 12 + 63) >> 6) << 6;
-        const int nchunks = (h + CTA_ROWS - 1) / CTA_ROWS;
+        const int pitch = cta_pitch(mis0, gp->w, cls);
+        const int rps = pitch <= pitch_max ? CTA_ROWS : slot_bytes / pitch;       // source rows per ring slot
+        const int nchunks = (h + rps - 1) / rps;
         const unsigned dsc = desc_s + hb * desc_bytes;
         out.pad_rows(roi, 0, dy0, tid, nthc);                       // whole rows above / below: contiguous runs
         out.pad_rows(roi, dy0 + new_h, T, tid, nthc);
@@ -1174,8 +1225,8 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty_s + 8 * j);
                 int ndone;
-                if (cls == 1) {
-                    const float ba = (lane < CTA_ROWS) ? lds_f32(dsc + 8u * (unsigned)(c * CTA_ROWS + lane)) : 0.f;
+                if (cls != 3) {
+                    const float ba = (lane < rps) ? lds_f32(dsc + 8u * (unsigned)(c * rps + lane)) : 0.f;
                     ndone = __popc(__ballot_sync(0xffffffffu, __float_as_int(ba) < 0));
                 } else {
                     // output rows whose second source row lies in this slot (monotone in y)
@@ -1261,6 +1312,79 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
                     }
                 }
             }
+        } else if (cls == 4) {
+            // ---------------- class 4: area, 4 .. 6 taps per axis, source rows in order ----------------
+            const int xn = __float_as_int(xd.w) >> 24;
+            const int nt = warp_max_i32(xn);                      // uniform: taps evaluated per source row
+            float w[6], cc[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                w[k] = (k == 0) ? xd.x : ((k < xn - 1) ? xd.y : ((k == xn - 1) ? xd.z : 0.f));
+                if (!active) w[k] = 0.f;
+                cc[k] = __fmul_rn(w[k], -8388608.0f);
+                if (!active && k == 0) cc[k] = 256.f;             // beside the image: every row sums to 256 -> LUT entry 256 = fill
+                asm volatile("" : "+f"(cc[k]));
+            }
+            u64 acc01 = 0ull;
+            float acc2 = 0.f;
+            unsigned roff = 0;
+            int yout = 0;
+            auto vstep = [&](float ba, float bb, u64 h01, float h2) {
+                const float wa = fabsf(ba);
+                acc01 = fadd2(acc01, fprod2(pack2(wa, wa), h01, nz2));
+                acc2 = __fadd_rn(acc2, __fmul_rn(wa, h2));
+                if (__float_as_int(ba) < 0) {                       // output row complete
+                    float a0f, a1f;
+                    unpack2(acc01, a0f, a1f);
+                    if (OUT_U8) {
+                        if (active) out.px(roi, dy0 + yout, x, round_u8(a0f), round_u8(a1f), round_u8(acc2));
+                        else if (x < T) out.pad(roi, dy0 + yout, x);
+                        ++yout;
+                    } else {
+                        const unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
+                        if (store_ok) {
+                            float* o = optr + roff;
+                            stg_out<0>(o, lds_f32(swap ? l2 : l0));
+                            stg_out<1>(o + plane, lds_f32(l1 + 4 * LUT_STRIDE));
+                            stg_out<2>(o + 2 * plane, lds_f32((swap ? l0 : l2) + 8 * LUT_STRIDE));
+                        }
+                        roff += (unsigned)T;
+                    }
+                    acc01 = fprod2(pack2(bb, bb), h01, nz2);
+                    acc2 = __fmul_rn(bb, h2);
+                }
+            };
+            auto strip = [&](auto nt_c) {
+                constexpr int NT = decltype(nt_c)::value;
+                for (int c = 0; c < nchunks; ++c, ++cg) {
+                    const unsigned j = cg % CTA_NSLOT;
+                    mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
+                    const unsigned rbase = ring_s + j * slot_bytes + colc4;
+                    const unsigned rec = dsc + 8u * (unsigned)(c * rps);
+                    int r = 0;
+                    for (; r + 1 < rps; r += 2) {                   // two rows at a time: their loads and conversions interleave
+                        const float4 d = make_float4(lds_f32(rec + 8u * r), lds_f32(rec + 8u * r + 4), lds_f32(rec + 8u * r + 8), lds_f32(rec + 8u * r + 12));
+                        u64 ha01, hb01;
+                        float ha2, hb2;
+                        h_area_n<NT>(rbase + (unsigned)(r * pitch), shc, w, cc, ha01, ha2);
+                        h_area_n<NT>(rbase + (unsigned)((r + 1) * pitch), shc, w, cc, hb01, hb2);
+                        vstep(d.x, d.y, ha01, ha2);
+                        vstep(d.z, d.w, hb01, hb2);
+                    }
+                    if (r < rps) {
+                        const float ba = lds_f32(rec + 8u * r), bb = lds_f32(rec + 8u * r + 4);
+                        u64 ha01;
+                        float ha2;
+                        h_area_n<NT>(rbase + (unsigned)(r * pitch), shc, w, cc, ha01, ha2);
+                        vstep(ba, bb, ha01, ha2);
+                    }
+                    __syncwarp();                               // every lane has read slot j
+                    if (lane == 0) mbar_arrive(empty_s + 8 * j);
+                }
+            };
+            if (nt <= 4) strip(std::integral_constant<int, 4>{});
+            else if (nt == 5) strip(std::integral_constant<int, 5>{});
+            else strip(std::integral_constant<int, 6>{});
         } else {
             // ---------------- class 3: fixed-point bilinear ----------------
             const int xw0 = __float_as_int(xd.x), xw1 = __float_as_int(xd.y);
@@ -1616,10 +1740,10 @@ static int cta_tensor_maps(const uint8_t* images, int B, int H, int W, CtaMaps* 
     return BPC_OK;
 }
 
-// workspace: geom[R] | xdesc[R][ds] | ydesc[R][ds + 8] | counters[16] | glist[R] | list1[R]    (ds = desc_stride(T), float4 records)
+// workspace: geom[R] | xdesc[R][ds] | ydesc[R][ydesc_stride(T)] | counters[16] | glist[R] | list1[R]    (ds = desc_stride(T), float4 records)
 static size_t ws_off_xdesc(int R) { return (((size_t)R * sizeof(RoiGeom)) + 15) & ~(size_t)15; }
 static size_t ws_off_ydesc(int R, int T) { return ws_off_xdesc(R) + (size_t)R * desc_stride(T) * sizeof(float4); }
-static size_t ws_off_count(int R, int T) { return ws_off_ydesc(R, T) + (size_t)R * (desc_stride(T) + 8) * sizeof(float4); }
+static size_t ws_off_count(int R, int T) { return ws_off_ydesc(R, T) + (size_t)R * ydesc_stride(T) * sizeof(float4); }
 static size_t crop_workspace_bytes(int R, int T) { return ws_off_count(R, T) + 64 + 2 * (size_t)R * sizeof(int32_t) + 64; }
 
 template <bool OUT_U8>
@@ -1648,7 +1772,7 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
     const bool aligned = ((long long)W * 3) % 16 == 0 && (long long)W * 3 >= TMAP_MAX_PITCH;
     // class 1 through the warp-specialised CTA kernel: 2-D TMA staging, at most eight strips, full-width boxes inside the pool rows
     const bool use_cta = aligned && T <= CTA_MAX_T && (long long)W * 3 >= cta_pitch_max(T);
-    bpc_crop_prep_kernel<<<R, 256, 0, st>>>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, aligned ? 1 : 0, geom, xdesc, ydesc,
+    bpc_crop_prep_kernel<<<R, 256, 0, st>>>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, (aligned ? 1 : 0) | (use_cta ? 2 : 0), geom, xdesc, ydesc,
                                             glist, gcount, status, use_cta ? list1 : nullptr);
     BPC_LAUNCH_CHECK();
     const uchar4 f4 = make_uchar4(fill[0], fill[1], fill[2], 0);
