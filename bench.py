@@ -308,6 +308,27 @@ def _peak():
     return peak, src
 
 
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """Libraries (the NCCL version banner, torch's c10d logs) write to file descriptor 1; stdout must carry exactly one JSON line.
+    From here on fd 1 points at stderr and the line goes out through a saved copy of the original descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(text):
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        print(text, flush=True)
+    else:
+        os.write(_REAL_STDOUT, (text + '\n').encode())
+
+
 def _measured_traffic(workload_key):
     """DRAM bytes of one crop launch from the committed ncu capture of the CURRENT kernel (profiles/crop_traffic.json,
     written by tools/ncu_summary.py --traffic): {workload key: {"dram_bytes": ..., "source": ...}}."""
@@ -464,6 +485,7 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    _guard_stdout()
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm')
     torch.cuda.set_device(local)
@@ -678,7 +700,7 @@ def main():
         achieved = per_launch_bytes / avg_launch_s / 1e9
         default_wl = (D, T, args.chunk_rois, args.pool, args.p_drop, args.sigma) == (20, 224, 16384, 8, 0.0, 1.0)
         traffic, traffic_src = _measured_traffic('config2_chunk16384_T224') if default_wl else (None, None)
-        roofline = {'bound': 'hbm', 'kernel': 'bpc_crop_warp_kernel<false,224,true,true> (+ prep, generic)', 'achieved': achieved,
+        roofline = {'bound': 'hbm', 'kernel': 'bpc_crop_cta_kernel<false,224,true> (+ bpc_crop_prep_kernel and the empty per-strip / generic launches)', 'achieved': achieved,
                     'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': traffic,
                     'traffic_source': traffic_src, 'peak_source': peak_src,
                     'algorithmic_bytes_per_launch': per_launch_bytes, 'avg_launch_ms': avg_launch_s * 1e3,
@@ -714,7 +736,7 @@ def main():
         line['weak_config2'] = weak
     if crop_gather is not None:
         line['crop_gather'] = crop_gather
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 

@@ -217,3 +217,48 @@ def test_torch_extension_loads_and_registers_its_operators():
     assert tuple(crops.shape) == (108, 3, 32, 32) and crops.dtype == torch.float32 and tuple(status.shape) == (108,)
     with pytest.raises(NotImplementedError):            # no CPU kernel: a CPU tensor cannot fall back to anything
         o.box_centers(torch.zeros((3, 4), dtype=torch.int32))
+
+
+def test_install_rebinds_every_hot_path_name_of_the_real_reference(lib):
+    """install() against the UNMODIFIED reference package (authoring container only: /root/reference does not travel to the GPU
+    box): every hot-path name that bpc/inference/process_pose.py:23-26 bound with `from ... import`, the defining modules'
+    own names, and PoseEstimator._match must point at this package afterwards; uninstall() restores them."""
+    import os
+    import sys
+    if not os.path.isdir('/root/reference/bpc'):
+        pytest.skip('/root/reference is not present on this machine')
+    from oracle.make_golden import import_reference
+    import bpc_baseline_b200 as pkg
+    ref = import_reference()
+    before = {name: getattr(ref.pp, name) for name in ('compute_cost_matrix', 'match_objects', 'triangulate_multi_view',
+                                                      'compute_fundamental_matrix', 'letterbox_preserving_aspect_ratio', 'PosePrediction')}
+    ref_match = ref.pp.PoseEstimator._match
+    try:
+        done = pkg.install('bpc')
+        for name in before:                                     # process_pose.py:23-26 (+ its own PosePrediction)
+            assert f'bpc.inference.process_pose.{name}' in done
+            assert getattr(ref.pp, name).__module__.startswith('bpc_baseline_b200.'), name
+        for mod, names in ((ref.em, ('epipolar_error', 'epipolar_error_full', 'compute_cost_matrix', 'match_objects', 'triangulate_multi_view')),
+                           (ref.cu, ('compute_fundamental_matrix',)), (ref.tri, ('triangulate_multi_view', 'compute_reprojection_error')),
+                           (ref.du, ('letterbox_preserving_aspect_ratio',))):
+            for name in names:
+                assert getattr(mod, name).__module__.startswith('bpc_baseline_b200.'), (mod.__name__, name)
+        assert 'bpc.inference.process_pose.PoseEstimator._match' in done and ref.pp.PoseEstimator._match is not ref_match
+        # every name the reference's process_pose imports from the hot-path modules is covered by the patch list
+        import ast
+        src = open('/root/reference/bpc/inference/process_pose.py').read()
+        hot = {'bpc.utils.data_utils': {'letterbox_preserving_aspect_ratio'}, 'bpc.inference.epipolar_matching': None,
+               'bpc.inference.utils.camera_utils': {'compute_fundamental_matrix'}}
+        for node in ast.walk(ast.parse(src)):
+            if isinstance(node, ast.ImportFrom) and node.module in hot:
+                for alias in node.names:
+                    if hot[node.module] is None or alias.name in hot[node.module]:
+                        assert f'bpc.inference.process_pose.{alias.asname or alias.name}' in done, alias.name
+        pkg.uninstall()
+        for name, fn in before.items():
+            assert getattr(ref.pp, name) is fn
+        assert ref.pp.PoseEstimator._match is ref_match
+    finally:
+        pkg.uninstall()
+        for m in [k for k in sys.modules if k == 'bpc' or k.startswith('bpc.')]:
+            sys.modules.pop(m, None)
