@@ -38,6 +38,7 @@ SIGNATURES = {
     'bpc_roi_crop_workspace_bytes': (_sz, [_i, _i]),
     'bpc_roi_crop': (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
     'bpc_roi_crop_u8': (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    'bpc_roi_crop_bf16': (_i, [_p, _i, _i, _i, _p, _i, _p, _i, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
     'bpc_normalise_lut': (_i, [_p, _p, _p, _p]),
     'bpc_crops_normalise': (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
 }

@@ -382,6 +382,39 @@ def roi_crop(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(255, 
     return out
 
 
+def roi_crop_bf16(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(255, 255, 255), swap_rb: bool = True,
+                  lut: Optional[torch.Tensor] = None, n_rois: Optional[torch.Tensor] = None, roi_first: int = 0,
+                  out: Optional[torch.Tensor] = None, status: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Network inputs as a bfloat16 tensor of logical shape [R,3,T,T] in ``torch.channels_last`` memory format (memory
+    [R,T,T,3]): :func:`roi_crop`'s float32 values rounded to bfloat16 -- what a bf16 tensor-core pose head reads, at half the
+    output bytes and without a layout pass.  ``out``: a bfloat16 [>=R,3,T,T] tensor that is channels_last-contiguous.
+    Raises for image pools the 2-D TMA path cannot take (row pitch not a multiple of 16 bytes, T > 256): use roi_crop there."""
+    B, H, W, R, f = _crop_args(images, rois, T, fill)
+    dev = images.device
+    if lut is None:
+        lut = normalise_lut(dev)
+    _chk(lut, torch.float32, 'lut', 2)
+    if out is None:
+        out = torch.empty((R, 3, T, T), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+    else:
+        if out.dtype != torch.bfloat16 or not out.is_cuda or out.dim() != 4 or out.shape[0] < R or tuple(out.shape[1:]) != (3, T, T) \
+                or not out.is_contiguous(memory_format=torch.channels_last):
+            raise RuntimeError('out must be a channels_last bfloat16 CUDA tensor [>=R,3,T,T]')
+    if status is not None:
+        _chk(status, torch.int32, 'status', 1)
+    if n_rois is not None:
+        _chk(n_rois, torch.int32, 'n_rois')
+    ws = _crop_workspace(dev, min(R, MAX_ROIS_PER_LAUNCH), T)
+    with torch.cuda.device(dev):
+        for lo in range(0, R, MAX_ROIS_PER_LAUNCH):
+            r = min(MAX_ROIS_PER_LAUNCH, R - lo)
+            _lib.check(_lib.load().bpc_roi_crop_bf16(_p(images), B, H, W, _p(rois[lo:lo + r]), r, _p(n_rois), int(roi_first) + lo, int(T),
+                                                     f, int(bool(swap_rb)), _p(lut), out[lo:lo + r].data_ptr(),
+                                                     _p(status[lo:lo + r]) if status is not None else None,
+                                                     _p(ws), ws.numel(), _stream(dev)), 'bpc_roi_crop_bf16')
+    return out
+
+
 def roi_crop_u8(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(255, 255, 255),
                    n_rois: Optional[torch.Tensor] = None, roi_first: int = 0, out: Optional[torch.Tensor] = None,
                 status: Optional[torch.Tensor] = None) -> torch.Tensor:

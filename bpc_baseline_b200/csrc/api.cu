@@ -13,6 +13,7 @@ extern "C" const char* bpc_error_string(int code) {
         case BPC_EINVAL: return "invalid argument (size, null pointer or unsupported value)";
         case BPC_EALIGN: return "pointer is not aligned as documented in bpc_b200.h";
         case BPC_EWORKSPACE: return "workspace too small";
+        case BPC_EUNSUPPORTED: return "this variant does not exist for the configuration (see include/bpc_b200.h)";
         case BPC_ETOOBIG: return "problem exceeds a documented limit (BPC_MAX_DET, BPC_MAX_ROI_WIDTH, shared memory)";
         default: break;
     }

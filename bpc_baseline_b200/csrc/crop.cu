@@ -323,8 +323,8 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
         if (g.cls == 2) glist[atomicAdd(gcount, 1)] = roi;
         if (list1 != nullptr) {
             // crops streamed by bpc_crop_cta_kernel from the front of the list, those of bpc_crop_warp_kernel from its back
-            if (g.cls == 1 || g.cls == 3 || g.cls == 4) list1[atomicAdd(gcount + 8, 1)] = roi;
-            else if (g.cls == 0) list1[R - 1 - atomicAdd(gcount + 9, 1)] = roi;
+            if (g.cls == 0 || g.cls == 1 || g.cls == 3 || g.cls == 4) list1[atomicAdd(gcount + 8, 1)] = roi;
+            else if (g.cls != 2 && g.cls != -1) list1[R - 1 - atomicAdd(gcount + 9, 1)] = roi;      // (none today)
         }
         geom[roi] = g;
     }
@@ -333,7 +333,14 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
 // ------------------------------------------------------------------------------------------------------
 // shared output helpers
 // ------------------------------------------------------------------------------------------------------
-template <bool OUT_U8>
+__device__ __forceinline__ unsigned short bf16_bits(float v) {       // round-to-nearest-even float32 -> bfloat16
+    unsigned short r;
+    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(v));
+    return r;
+}
+
+// BF16: the float path's values rounded to bfloat16 and stored channels-last ([R][T][T][3], what a bf16 tensor-core network reads)
+template <bool OUT_U8, bool BF16 = false>
 struct Out {
     float* outf; uint8_t* outb;
     const float* lut;           // shared memory [3][LUT_STRIDE]
@@ -347,16 +354,24 @@ struct Out {
             o[0] = (uint8_t)b0; o[1] = (uint8_t)b1; o[2] = (uint8_t)b2;
         } else {
             const int s0 = swap_rb ? b2 : b0, s2 = swap_rb ? b0 : b2;
-            float* o = outf + ((size_t)roi * 3 * T + y) * T + x;
-            o[0] = lut[s0];
-            o[(size_t)T * T] = lut[LUT_STRIDE + b1];
-            o[(size_t)2 * T * T] = lut[2 * LUT_STRIDE + s2];
+            if (BF16) {
+                unsigned short* o = reinterpret_cast<unsigned short*>(outf) + (((size_t)roi * T + y) * T + x) * 3;
+                o[0] = bf16_bits(lut[s0]); o[1] = bf16_bits(lut[LUT_STRIDE + b1]); o[2] = bf16_bits(lut[2 * LUT_STRIDE + s2]);
+            } else {
+                float* o = outf + ((size_t)roi * 3 * T + y) * T + x;
+                o[0] = lut[s0];
+                o[(size_t)T * T] = lut[LUT_STRIDE + b1];
+                o[(size_t)2 * T * T] = lut[2 * LUT_STRIDE + s2];
+            }
         }
     }
     __device__ __forceinline__ void pad(int roi, int y, int x) const {
         if (OUT_U8) {
             uint8_t* o = outb + (((size_t)roi * T + y) * T + x) * 3;
             o[0] = fillc[0]; o[1] = fillc[1]; o[2] = fillc[2];
+        } else if (BF16) {
+            unsigned short* o = reinterpret_cast<unsigned short*>(outf) + (((size_t)roi * T + y) * T + x) * 3;
+            o[0] = bf16_bits(padf[0]); o[1] = bf16_bits(padf[1]); o[2] = bf16_bits(padf[2]);
         } else {
             float* o = outf + ((size_t)roi * 3 * T + y) * T + x;
             o[0] = padf[0]; o[(size_t)T * T] = padf[1]; o[(size_t)2 * T * T] = padf[2];
@@ -369,6 +384,17 @@ struct Out {
             uint8_t* o = outb + ((size_t)roi * T + ra) * T * 3;
             const int nbytes = (rb - ra) * T * 3;
             for (int e = tid; e < nbytes; e += nth) o[e] = fillc[e % 3];
+        } else if (BF16) {
+            unsigned short* o = reinterpret_cast<unsigned short*>(outf) + ((size_t)roi * T + ra) * T * 3;
+            const int n = (rb - ra) * T * 3;
+            const unsigned short f0 = bf16_bits(padf[0]), f1 = bf16_bits(padf[1]), f2 = bf16_bits(padf[2]);
+            if ((((size_t)(uintptr_t)o) & 3) == 0 && (n & 1) == 0) {          // 32-bit stores of the period-3 pattern
+                unsigned* o2 = reinterpret_cast<unsigned*>(o);
+                const unsigned p0 = f0 | ((unsigned)f1 << 16), p1 = f2 | ((unsigned)f0 << 16), p2 = f1 | ((unsigned)f2 << 16);
+                for (int e = tid; e < (n >> 1); e += nth) { const int m = e % 3; o2[e] = m == 0 ? p0 : (m == 1 ? p1 : p2); }
+            } else {
+                for (int e = tid; e < n; e += nth) { const int m = e % 3; o[e] = m == 0 ? f0 : (m == 1 ? f1 : f2); }
+            }
         } else if ((T & 3) == 0) {
             const int n4 = (rb - ra) * (T >> 2);
             for (int p = 0; p < 3; ++p) {
@@ -386,8 +412,8 @@ struct Out {
     }
 };
 
-template <bool OUT_U8>
-__device__ __forceinline__ void out_init(Out<OUT_U8>& o, float* outf, uint8_t* outb, const float* lut_s, int T, int swap_rb, uchar4 fill) {
+template <bool OUT_U8, bool BF16>
+__device__ __forceinline__ void out_init(Out<OUT_U8, BF16>& o, float* outf, uint8_t* outb, const float* lut_s, int T, int swap_rb, uchar4 fill) {
     o.outf = outf; o.outb = outb; o.lut = lut_s; o.T = T; o.swap_rb = swap_rb;
     o.fillc[0] = fill.x; o.fillc[1] = fill.y; o.fillc[2] = fill.z;
     if (!OUT_U8)
@@ -1082,7 +1108,7 @@ __host__ __device__ __forceinline__ int cta_smem_bytes(int T) { return LUT_SMEM 
 
 __device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
 
-template <bool OUT_U8, int TT, bool SWAP>
+template <bool OUT_U8, int TT, bool SWAP, bool BF16 = false>
 __global__ void __launch_bounds__(288, 3)
 bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom,
                     const float4* __restrict__ xdesc, const float4* __restrict__ ydesc, const int32_t* __restrict__ list1,
@@ -1110,7 +1136,7 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
     if (!OUT_U8)
         for (int e = tid; e < 768; e += (int)blockDim.x) lut[(e >> 8) * LUT_STRIDE + (e & 255)] = lut_g[e];
     __syncthreads();
-    Out<OUT_U8> out;
+    Out<OUT_U8, BF16> out;
     out_init(out, outf, outb, lut, T, swap_rb, fill);
     if (!OUT_U8 && tid < 3) lut[tid * LUT_STRIDE + 256] = out.padf[tid];
     __syncthreads();
@@ -1138,18 +1164,20 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
             const int roi = list1[idx];
             const RoiGeom* gp = geom + roi;
             const unsigned long long src = gp->src;
-            const int w = gp->w, h = gp->h;
+            const int w = gp->w, h = gp->cls == 0 ? 0 : gp->h;     // a rejected box (class 0) has no source rows: header only
             hdr[hb] = roi;
             // the part of the crop's row-descriptor block that will be read: per output row (class 3) or per source row, padded slot included
-            const unsigned dbytes = (unsigned)min(desc_bytes, gp->cls == 3 ? 16 * (gp->new_h + 1) : 8 * (((h + CTA_ROWS - 1) & ~(CTA_ROWS - 1)) + CTA_ROWS));
+            const unsigned dbytes = gp->cls == 0 ? 0u : (unsigned)min(desc_bytes, gp->cls == 3 ? 16 * (gp->new_h + 1) : 8 * (((h + CTA_ROWS - 1) & ~(CTA_ROWS - 1)) + CTA_ROWS));
             mbar_expect_tx(hfull_s + 8 * hb, dbytes);
-            bulk_g2s(desc_s + hb * desc_bytes, (unsigned long long)(uintptr_t)(ydesc + (size_t)roi * ystride), dbytes, hfull_s + 8 * hb);
+            if (dbytes) bulk_g2s(desc_s + hb * desc_bytes, (unsigned long long)(uintptr_t)(ydesc + (size_t)roi * ystride), dbytes, hfull_s + 8 * hb);
             const int mis0 = (int)(src & 15ull);
             const int pitch = cta_pitch(mis0, w, gp->cls);
             const unsigned long long off = (src & ~15ull) - (unsigned long long)(uintptr_t)images;
             const int row0 = (int)(off / rowstride);
             const int x8 = (int)((off - (unsigned long long)row0 * rowstride) >> 3);
-            if (pitch <= pitch_max) {
+            if (gp->cls == 0) {
+                // nothing to stage
+            } else if (pitch <= pitch_max) {
                 // one 2-D tensor copy of eight full-width rows per slot (rows / columns beyond the pool are zero-filled)
                 const CUtensorMap* map = &tm.m[(pitch >> 6) - 1];
                 const int nchunks = (h + CTA_ROWS - 1) / CTA_ROWS;
@@ -1209,6 +1237,12 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
         const int rps = pitch <= pitch_max ? CTA_ROWS : slot_bytes / pitch;       // source rows per ring slot
         const int nchunks = (h + rps - 1) / rps;
         const unsigned dsc = desc_s + hb * desc_bytes;
+        if (cls == 0) {                                             // rejected box: the whole canvas is fill (no slots were issued)
+            out.pad_rows(roi, 0, T, tid, nthc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(hempty_s + 8 * hb);
+            continue;
+        }
         out.pad_rows(roi, 0, dy0, tid, nthc);                       // whole rows above / below: contiguous runs
         out.pad_rows(roi, dy0 + new_h, T, tid, nthc);
         const int xr = x - dx0;
@@ -1216,6 +1250,8 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
         const bool touches = wid * 32 < dx0 + new_w && wid * 32 + 32 > dx0;
         const bool store_ok = (TT && TT % 32 == 0) || x < T;
         float* optr = outf + ((size_t)roi * 3 * T + dy0) * T + x;     // (plane 0, first image row, column x)
+        unsigned short* optr16 = reinterpret_cast<unsigned short*>(outf) + (((size_t)roi * T + dy0) * T + x) * 3;   // BF16: pixel (row, x), channels-last
+        const unsigned short padh0 = bf16_bits(out.padf[0]), padh1 = bf16_bits(out.padf[1]), padh2 = bf16_bits(out.padf[2]);
         if (!touches) {
             // a strip beside the resized image: the fill value, at the pace of the neighbours
             int ydone = 0;
@@ -1243,6 +1279,7 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
                 if (store_ok)
                     for (int r = 0; r < ndone; ++r) {
                         if (OUT_U8) out.pad(roi, dy0 + ydone + r, x);
+                        else if (BF16) { optr16[0] = padh0; optr16[1] = padh1; optr16[2] = padh2; optr16 += 3 * T; }
                         else { optr[0] = out.padf[0]; optr[plane] = out.padf[1]; optr[2 * plane] = out.padf[2]; optr += T; }
                     }
                 ydone += ndone;
@@ -1299,12 +1336,16 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
                             } else {
                                 const unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
                                 if (store_ok) {
-                                    float* o = optr + roff;
-                                    stg_out<0>(o, lds_f32(swap ? l2 : l0));
-                                    stg_out<1>(o + plane, lds_f32(l1 + 4 * LUT_STRIDE));
-                                    stg_out<2>(o + 2 * plane, lds_f32((swap ? l0 : l2) + 8 * LUT_STRIDE));
+                                    const float v0 = lds_f32(swap ? l2 : l0), v1 = lds_f32(l1 + 4 * LUT_STRIDE), v2 = lds_f32((swap ? l0 : l2) + 8 * LUT_STRIDE);
+                                    if (BF16) {
+                                        unsigned short* o = optr16 + roff;
+                                        o[0] = bf16_bits(v0); o[1] = bf16_bits(v1); o[2] = bf16_bits(v2);
+                                    } else {
+                                        float* o = optr + roff;
+                                        stg_out<0>(o, v0); stg_out<1>(o + plane, v1); stg_out<2>(o + 2 * plane, v2);
+                                    }
                                 }
-                                roff += (unsigned)T;
+                                roff += BF16 ? 3u * (unsigned)T : (unsigned)T;
                             }
                             acc01 = fprod2(pack2(bb[k], bb[k]), h01[k], nz2);
                             acc2 = __fmul_rn(bb[k], h2[k]);
@@ -1343,12 +1384,16 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
                     } else {
                         const unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
                         if (store_ok) {
-                            float* o = optr + roff;
-                            stg_out<0>(o, lds_f32(swap ? l2 : l0));
-                            stg_out<1>(o + plane, lds_f32(l1 + 4 * LUT_STRIDE));
-                            stg_out<2>(o + 2 * plane, lds_f32((swap ? l0 : l2) + 8 * LUT_STRIDE));
+                            const float v0 = lds_f32(swap ? l2 : l0), v1 = lds_f32(l1 + 4 * LUT_STRIDE), v2 = lds_f32((swap ? l0 : l2) + 8 * LUT_STRIDE);
+                            if (BF16) {
+                                unsigned short* o = optr16 + roff;
+                                o[0] = bf16_bits(v0); o[1] = bf16_bits(v1); o[2] = bf16_bits(v2);
+                            } else {
+                                float* o = optr + roff;
+                                stg_out<0>(o, v0); stg_out<1>(o + plane, v1); stg_out<2>(o + 2 * plane, v2);
+                            }
                         }
-                        roff += (unsigned)T;
+                        roff += BF16 ? 3u * (unsigned)T : (unsigned)T;
                     }
                     acc01 = fprod2(pack2(bb, bb), h01, nz2);
                     acc2 = __fmul_rn(bb, h2);
@@ -1422,13 +1467,19 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
                         if (OUT_U8) {
                             out.px(roi, dy0 + y - 1, x, (int)(o[0] >> 2) & 255, (int)(o[1] >> 2) & 255, (int)(o[2] >> 2) & 255);
                         } else {
-                            stg_out<0>(optr, lds_f32(lut_s + ((swap ? o[2] : o[0]) & 0x3fcu)));
-                            stg_out<1>(optr + plane, lds_f32(lut_s + 4 * LUT_STRIDE + (o[1] & 0x3fcu)));
-                            stg_out<2>(optr + 2 * plane, lds_f32(lut_s + 8 * LUT_STRIDE + ((swap ? o[0] : o[2]) & 0x3fcu)));
-                            optr += T;
+                            const float v0 = lds_f32(lut_s + ((swap ? o[2] : o[0]) & 0x3fcu)), v1 = lds_f32(lut_s + 4 * LUT_STRIDE + (o[1] & 0x3fcu)),
+                                        v2 = lds_f32(lut_s + 8 * LUT_STRIDE + ((swap ? o[0] : o[2]) & 0x3fcu));
+                            if (BF16) {
+                                optr16[0] = bf16_bits(v0); optr16[1] = bf16_bits(v1); optr16[2] = bf16_bits(v2);
+                                optr16 += 3 * T;
+                            } else {
+                                stg_out<0>(optr, v0); stg_out<1>(optr + plane, v1); stg_out<2>(optr + 2 * plane, v2);
+                                optr += T;
+                            }
                         }
                     } else if (x < T) {
                         if (OUT_U8) out.pad(roi, dy0 + y - 1, x);
+                        else if (BF16) { optr16[0] = padh0; optr16[1] = padh1; optr16[2] = padh2; optr16 += 3 * T; }
                         else { optr[0] = out.padf[0]; optr[plane] = out.padf[1]; optr[2 * plane] = out.padf[2]; optr += T; }
                     }
                 }
@@ -1444,8 +1495,8 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
 // ------------------------------------------------------------------------------------------------------
 // generic kernel: any regime / scale, persistent CTAs over (ROI, band) items of the generic list
 // ------------------------------------------------------------------------------------------------------
-template <bool OUT_U8>
-__device__ void crop_generic_band(unsigned char* raw, YDesc* yd, const Out<OUT_U8>& out, const RoiGeom& g, int roi, int band,
+template <bool OUT_U8, bool BF16>
+__device__ void crop_generic_band(unsigned char* raw, YDesc* yd, const Out<OUT_U8, BF16>& out, const RoiGeom& g, int roi, int band,
                                   const uint8_t* __restrict__ images, int B, int H, int W, int T, int tid, int nth) {
     const int x = tid;
     const bool incol = x < T;
@@ -1619,7 +1670,7 @@ __device__ void crop_generic_band(unsigned char* raw, YDesc* yd, const Out<OUT_U
     }
 }
 
-template <bool OUT_U8, int NTH>
+template <bool OUT_U8, int NTH, bool BF16 = false>
 __global__ void __launch_bounds__(NTH)
 bpc_crop_generic_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom,
                         const int32_t* __restrict__ glist, const int32_t* __restrict__ gcount, int T, int nbands,
@@ -1634,14 +1685,14 @@ bpc_crop_generic_kernel(const uint8_t* __restrict__ images, int B, int H, int W,
     if (!OUT_U8)
         for (int e = tid; e < 768; e += nth) lut[(e >> 8) * LUT_STRIDE + (e & 255)] = lut_g[e];
     __syncthreads();
-    Out<OUT_U8> out;
+    Out<OUT_U8, BF16> out;
     out_init(out, outf, outb, lut, T, swap_rb, fill);
     for (long long item = blockIdx.x; item < items; item += gridDim.x) {
         const int roi = glist[item / nbands], band = (int)(item % nbands);
         __syncthreads();
         if (tid == 0) g = geom[roi];
         __syncthreads();
-        crop_generic_band<OUT_U8>(raw, yd, out, g, roi, band, images, B, H, W, T, tid, nth);
+        crop_generic_band<OUT_U8, BF16>(raw, yd, out, g, roi, band, images, B, H, W, T, tid, nth);
     }
 }
 
@@ -1746,7 +1797,7 @@ static size_t ws_off_ydesc(int R, int T) { return ws_off_xdesc(R) + (size_t)R * 
 static size_t ws_off_count(int R, int T) { return ws_off_ydesc(R, T) + (size_t)R * ydesc_stride(T) * sizeof(float4); }
 static size_t crop_workspace_bytes(int R, int T) { return ws_off_count(R, T) + 64 + 2 * (size_t)R * sizeof(int32_t) + 64; }
 
-template <bool OUT_U8>
+template <bool OUT_U8, bool BF16 = false>
 static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R, const int32_t* n_rois_dev,
                        int roi_first, int T, const uint8_t* fill, int swap_rb, const float* lut, float* outf, uint8_t* outb,
                        int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
@@ -1772,6 +1823,7 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
     const bool aligned = ((long long)W * 3) % 16 == 0 && (long long)W * 3 >= TMAP_MAX_PITCH;
     // class 1 through the warp-specialised CTA kernel: 2-D TMA staging, at most eight strips, full-width boxes inside the pool rows
     const bool use_cta = aligned && T <= CTA_MAX_T && (long long)W * 3 >= cta_pitch_max(T);
+    if (BF16 && !use_cta) return BPC_EUNSUPPORTED;       // the bfloat16 output exists on the CTA kernel's path only
     bpc_crop_prep_kernel<<<R, 256, 0, st>>>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, (aligned ? 1 : 0) | (use_cta ? 2 : 0), geom, xdesc, ydesc,
                                             glist, gcount, status, use_cta ? list1 : nullptr);
     BPC_LAUNCH_CHECK();
@@ -1785,6 +1837,7 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
         const bool sw = swap_rb != 0;
         CtaFn fn;
         if (OUT_U8) fn = bpc_crop_cta_kernel<OUT_U8, 0, false>;
+        else if (BF16) fn = sw ? bpc_crop_cta_kernel<OUT_U8, 0, true, BF16> : bpc_crop_cta_kernel<OUT_U8, 0, false, BF16>;
         else if (T == 224) fn = sw ? bpc_crop_cta_kernel<OUT_U8, 224, true> : bpc_crop_cta_kernel<OUT_U8, 224, false>;
         else if (T == 256) fn = sw ? bpc_crop_cta_kernel<OUT_U8, 256, true> : bpc_crop_cta_kernel<OUT_U8, 256, false>;
         else fn = sw ? bpc_crop_cta_kernel<OUT_U8, 0, true> : bpc_crop_cta_kernel<OUT_U8, 0, false>;
@@ -1801,7 +1854,7 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
         fn<<<grid, threads, smem_bytes, st>>>(images, B, H, W, geom, xdesc, ydesc, list1, gcount, T, f4, swap_rb, lut, outf, outb, cmaps);
         BPC_LAUNCH_CHECK();
     }
-    {
+    if (!BF16) {
         typedef void (*WarpFn)(const uint8_t*, int, int, int, const RoiGeom*, const float4*, const float4*, int32_t*, int, int, int,
                                uchar4, int, const float*, float*, uint8_t*, const TmapSet, const int32_t*);
         TmapSet tmaps;
@@ -1837,14 +1890,14 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
     const int grid = (int)(max_items < 148 * 2 ? max_items : 148 * 2);
     const int threads = ((T + 31) / 32) * 32;                   // one thread per output column
     if (threads <= 256) {
-        e = cudaFuncSetAttribute(bpc_crop_generic_kernel<OUT_U8, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROP_RAW_BYTES);
+        e = cudaFuncSetAttribute(bpc_crop_generic_kernel<OUT_U8, 256, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROP_RAW_BYTES);
         if (e != cudaSuccess) return (int)e;
-        bpc_crop_generic_kernel<OUT_U8, 256><<<grid, threads, CROP_RAW_BYTES, st>>>(images, B, H, W, geom, glist, gcount, T, nbands, f4,
+        bpc_crop_generic_kernel<OUT_U8, 256, BF16><<<grid, threads, CROP_RAW_BYTES, st>>>(images, B, H, W, geom, glist, gcount, T, nbands, f4,
                                                                                    swap_rb, lut, outf, outb);
     } else {
-        e = cudaFuncSetAttribute(bpc_crop_generic_kernel<OUT_U8, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROP_RAW_BYTES);
+        e = cudaFuncSetAttribute(bpc_crop_generic_kernel<OUT_U8, 1024, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, CROP_RAW_BYTES);
         if (e != cudaSuccess) return (int)e;
-        bpc_crop_generic_kernel<OUT_U8, 1024><<<grid, threads, CROP_RAW_BYTES, st>>>(images, B, H, W, geom, glist, gcount, T, nbands, f4,
+        bpc_crop_generic_kernel<OUT_U8, 1024, BF16><<<grid, threads, CROP_RAW_BYTES, st>>>(images, B, H, W, geom, glist, gcount, T, nbands, f4,
                                                                                     swap_rb, lut, outf, outb);
     }
     BPC_LAUNCH_CHECK();
@@ -1864,6 +1917,15 @@ extern "C" int bpc_roi_crop(const uint8_t* images, int B, int H, int W, const in
     if (((uintptr_t)out & 15) != 0) return BPC_EALIGN;
     return launch_crop<false>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, fill, swap_rb, lut, out, nullptr, status,
                               workspace, workspace_bytes, stream);
+}
+
+extern "C" int bpc_roi_crop_bf16(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R,
+                                 const int32_t* n_rois_dev, int roi_first, int T, const uint8_t* fill, int swap_rb,
+                                 const float* lut, void* out, int32_t* status, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+    if (((uintptr_t)out & 15) != 0) return BPC_EALIGN;
+    return launch_crop<false, true>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, fill, swap_rb, lut, (float*)out, nullptr, status,
+                                    workspace, workspace_bytes, stream);
 }
 
 extern "C" int bpc_roi_crop_u8(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R,

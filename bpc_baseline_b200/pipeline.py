@@ -23,7 +23,8 @@ from ._host import nvtx_range
 class MatchCropPipeline:
     def __init__(self, S: int, Dmax: int, *, T: int = 224, chunk_rois: int = 16384, threshold=30,
                  swap_rb: bool = True, fill=(255, 255, 255), device='cuda', want_reproj: bool = True,
-                 reproj_thresh: Optional[float] = None, crops: Optional[torch.Tensor] = None):
+                 reproj_thresh: Optional[float] = None, crops: Optional[torch.Tensor] = None,
+                 crop_dtype: torch.dtype = torch.float32):
         self.S, self.D, self.T = int(S), int(Dmax), int(T)
         self.device = torch.device(device)
         self.threshold = threshold
@@ -32,7 +33,14 @@ class MatchCropPipeline:
         self.chunk = max(1, min(int(chunk_rois), self.cap))
         dev = self.device
         self.rois = torch.zeros((self.cap, 5), dtype=torch.int32, device=dev)
-        if crops is not None:                              # a caller-owned chunk buffer shared between pipelines
+        if crop_dtype not in (torch.float32, torch.bfloat16):
+            raise RuntimeError('crop_dtype must be torch.float32 or torch.bfloat16')
+        self.crop_dtype = crop_dtype
+        if crop_dtype == torch.bfloat16:                   # bf16 channels-last chunk buffer: the pose head's input as it stands
+            if crops is not None:
+                raise RuntimeError('a caller-owned chunk buffer is float32 only')
+            self.crops = torch.empty((self.chunk, 3, self.T, self.T), dtype=torch.bfloat16, device=dev, memory_format=torch.channels_last)
+        elif crops is not None:                            # a caller-owned chunk buffer shared between pipelines
             if crops.dtype != torch.float32 or not crops.is_contiguous() or crops.numel() < self.chunk * 3 * self.T * self.T:
                 raise RuntimeError('crops must be a contiguous float32 buffer of at least chunk_rois * 3 * T * T elements')
             self.crops = crops.view(-1)[:self.chunk * 3 * self.T * self.T].view(self.chunk, 3, self.T, self.T)
@@ -69,9 +77,9 @@ class MatchCropPipeline:
         for first in range(0, upto, self.chunk):
             r = min(self.chunk, self.cap - first)
             with nvtx_range('bpc.crop_chunk'):
-                out = batched.roi_crop(images, rois[first:first + r], T=self.T, fill=self.fill, swap_rb=self.swap_rb,
-                                       lut=self.lut, n_rois=total, roi_first=first, out=self.crops,
-                                       status=self.status[first:first + r])
+                crop = batched.roi_crop_bf16 if self.crop_dtype == torch.bfloat16 else batched.roi_crop
+                out = crop(images, rois[first:first + r], T=self.T, fill=self.fill, swap_rb=self.swap_rb,
+                           lut=self.lut, n_rois=total, roi_first=first, out=self.crops, status=self.status[first:first + r])
             launches += 1
             if consumer is not None:
                 consumer(out[:r], first)
@@ -198,9 +206,10 @@ class MatchCropPipeline:
         return int(sum(h[k].numel() * h[k].element_size() for k in ('idx', 'n', 'cost', 'X', 'n_rois')))
 
 
-def algorithmic_crop_bytes(rois: np.ndarray, T: int) -> int:
-    """per crop 3*h*w source bytes read once + 3*T*T*4 output bytes written once + 20 B record."""
+def algorithmic_crop_bytes(rois: np.ndarray, T: int, out_elem_bytes: int = 4) -> int:
+    """per crop 3*h*w source bytes read once + 3*T*T*4 output bytes written once + 20 B record
+    (``out_elem_bytes`` = 2 for the bfloat16 variant, 1 for the uint8 letterboxed image)."""
     rois = np.asarray(rois, np.int64)
     w = rois[:, 3] - rois[:, 1]
     h = rois[:, 4] - rois[:, 2]
-    return int((3 * w * h).sum() + len(rois) * (3 * T * T * 4 + 20))
+    return int((3 * w * h).sum() + len(rois) * (3 * T * T * out_elem_bytes + 20))

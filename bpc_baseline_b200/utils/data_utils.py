@@ -103,6 +103,98 @@ class Capture:
         return cls(images, Ks, RTs, obj_id, load_gt_poses(scene_dir, '', cam_ids, image_id, obj_id))
 
 
+class SceneBatch:
+    """Device-resident captures of S scenes x C cameras -- the matcher's and the crop kernels' input layout.
+
+    ``Ks`` float32 [S, C, 3, 3], ``RTs`` float64 [S, C, 4, 4], ``images`` uint8 [S * C, H, W, 3] BGR (image of scene s, camera
+    c at index s * C + c), all CUDA tensors; ``decoders`` names what decoded each image file."""
+
+    def __init__(self, Ks, RTs, images, decoders):
+        self.Ks, self.RTs, self.images, self.decoders = Ks, RTs, images, decoders
+
+    def capture(self, s, obj_id=None):
+        """Scene ``s`` as a host-side :class:`Capture` (a device -> host copy; for the single-scene drop-ins and tests)."""
+        C = self.Ks.shape[1]
+        return Capture([im for im in _host.to_host(self.images[s * C:(s + 1) * C])], [k for k in _host.to_host(self.Ks[s])],
+                       [rt for rt in _host.to_host(self.RTs[s])], obj_id)
+
+
+def load_scene_batch(scene_dirs, cam_ids, image_ids, decode='cv2'):
+    """Batched BOP loader: ``Capture.from_dir`` (reference data_utils.py:399-409) and ``load_camera_params``
+    (camera_utils.py:6-20) for S (scene_dir, image_id) pairs at once, landing in HBM as the tensors the batched API takes.
+
+    * intrinsics / extrinsics: ``scene_camera_<cam>.json`` is parsed once per directory; K, R, t are float32 as the reference
+      loads them, and RT is the float64 4x4 of ``calc_pose_matrix`` (:383-387) holding those float32-rounded values;
+      both are assembled in pinned host memory and copied with one asynchronous H2D each;
+    * images ``rgb_<cam>/<image_id:06d>.{png,jpg}``: ``decode='cv2'`` (default) decodes on the host exactly as the reference
+      does (``cv2.imread``, BGR) into a two-slot pinned staging buffer and overlaps each slot's asynchronous H2D with the next
+      file's decode; ``decode='nvjpeg'`` sends JPEG files through nvJPEG (``torchvision.io.decode_jpeg(device='cuda')``, library
+      code) straight to HBM and reorders RGB planes to BGR pixels on the device -- its IDCT is not bit-identical to libjpeg's,
+      so the pixels can differ from ``cv2.imread`` by one grey level; PNG (lossless) always takes the cv2 path.
+
+    Returns a :class:`SceneBatch`.  All images must share one size (one camera model per batch, as in BOP)."""
+    import cv2
+    import torch
+    scene_dirs, image_ids, cam_ids = list(scene_dirs), [int(i) for i in image_ids], list(cam_ids)
+    if len(scene_dirs) != len(image_ids):
+        raise ValueError('scene_dirs and image_ids must have one entry per scene')
+    if decode not in ('cv2', 'nvjpeg'):
+        raise ValueError("decode must be 'cv2' or 'nvjpeg'")
+    dev = _host.device()
+    S, C = len(scene_dirs), len(cam_ids)
+    Ks_h = torch.empty((S, C, 3, 3), dtype=torch.float32).pin_memory()
+    RTs_h = torch.empty((S, C, 4, 4), dtype=torch.float64).pin_memory()
+    Ks_n, RTs_n = Ks_h.numpy(), RTs_h.numpy()
+    params = {}
+    for s, (d, i) in enumerate(zip(scene_dirs, image_ids)):
+        if d not in params:
+            params[d] = load_camera_params(d, cam_ids)
+        for c, cam in enumerate(cam_ids):
+            Ks_n[s, c] = params[d][cam]['K'][i]
+            RTs_n[s, c] = calc_pose_matrix(params[d][cam]['R'][i], params[d][cam]['t'][i])      # float32 -> float64 widening
+    Ks = Ks_h.to(dev, non_blocking=True)
+    RTs = RTs_h.to(dev, non_blocking=True)
+
+    files = []
+    for d, i in zip(scene_dirs, image_ids):
+        for cam in cam_ids:
+            hits = sorted(glob.glob(os.path.join(d, f"rgb_{cam}", f"{i:06d}.*g")))
+            if not hits:
+                raise FileNotFoundError(os.path.join(d, f"rgb_{cam}", f"{i:06d}.*g"))
+            files.append(hits[0])
+    images, stage, events, decoders = None, None, [None, None], []
+    for n, path in enumerate(files):
+        if decode == 'nvjpeg' and path.lower().endswith(('.jpg', '.jpeg')):
+            from torchvision.io import ImageReadMode, decode_jpeg, read_file
+            rgb = decode_jpeg(read_file(path), mode=ImageReadMode.RGB, device=dev)              # [3, H, W] in HBM
+            if images is None:
+                images = torch.empty((len(files), rgb.shape[1], rgb.shape[2], 3), dtype=torch.uint8, device=dev)
+            if tuple(rgb.shape[1:]) != tuple(images.shape[1:3]):
+                raise ValueError(f'{path}: image size differs from the first image of the batch')
+            images[n].copy_(rgb.flip(0).permute(1, 2, 0))
+            decoders.append('nvjpeg')
+            continue
+        img = cv2.imread(path)
+        if img is None:
+            raise IOError(f'cannot decode {path}')
+        if images is None:
+            images = torch.empty((len(files),) + img.shape, dtype=torch.uint8, device=dev)
+        if img.shape != tuple(images.shape[1:]):
+            raise ValueError(f'{path}: image size differs from the first image of the batch')
+        if stage is None:
+            stage = torch.empty((2,) + img.shape, dtype=torch.uint8).pin_memory()
+        k = n & 1
+        if events[k] is not None:
+            events[k].synchronize()                         # the slot's previous upload has left pinned memory
+        np.copyto(stage[k].numpy(), img)
+        images[n].copy_(stage[k], non_blocking=True)
+        events[k] = torch.cuda.Event()
+        events[k].record()
+        decoders.append('cv2+pinned')
+    torch.cuda.current_stream().synchronize()               # pinned staging goes out of scope below
+    return SceneBatch(Ks, RTs, images, decoders)
+
+
 def draw_crop_jitter(bbox_visib, rnd=None):
     """The three draws BOPSingleObjDataset.__getitem__ makes per sample, in its order (data_utils.py:257-263):
     ``scale_factor = 1.0 + 0.2 * random.random()``, then ``randint`` for shift_x and shift_y within +-int(0.1 * side).

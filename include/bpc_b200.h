@@ -39,7 +39,8 @@ enum {
     BPC_EINVAL = -1,     /* bad size / null pointer / unsupported value */
     BPC_EALIGN = -2,     /* pointer not aligned as documented */
     BPC_EWORKSPACE = -3, /* workspace too small */
-    BPC_ETOOBIG = -4     /* problem exceeds a documented limit (Dmax, ROI width) */
+    BPC_ETOOBIG = -4,    /* problem exceeds a documented limit (Dmax, ROI width) */
+    BPC_EUNSUPPORTED = -5 /* the variant does not exist for this configuration (see the entry point's comment) */
 };
 
 /* per-scene status values of the `n` output of the matchers (any negative n: the scene has no matches) */
@@ -229,6 +230,15 @@ int bpc_roi_crop_u8(const uint8_t* images, int B, int H, int W, const int32_t* r
                     const int32_t* n_rois_dev, int roi_first, int T, const uint8_t* fill,
                     uint8_t* out, int32_t* status,
                     void* workspace, size_t workspace_bytes, void* stream);
+/* bpc_roi_crop_bf16: the network-input variant for a bf16 tensor-core pose head (process_pose.py:210-212 moves the float32
+ * tensor to the GPU and runs SimplePoseNet on it): every value of bpc_roi_crop's float32 tensor rounded to bfloat16
+ * (round-to-nearest-even) and stored channels-last, out = bfloat16 [R][T][T][3] (16-byte aligned) -- half the output bytes,
+ * no layout pass before the first convolution.  Exists on the 2-D-TMA path only: image row pitch W*3 a multiple of 16 bytes
+ * and >= 1600, T <= 256; otherwise BPC_EUNSUPPORTED (use bpc_roi_crop). */
+int bpc_roi_crop_bf16(const uint8_t* images, int B, int H, int W, const int32_t* rois, int R,
+                      const int32_t* n_rois_dev, int roi_first, int T, const uint8_t* fill, int swap_rb,
+                      const float* lut, void* out, int32_t* status,
+                      void* workspace, size_t workspace_bytes, void* stream);
 /* lut[c][v] = (v/255 - mean[c]) / std[c] in float32 with true divisions, as torchvision's
  * to_tensor (.div(255)) + normalize (.sub_(mean).div_(std)); process_pose.py:207-209. */
 int bpc_normalise_lut(const float* mean_host3, const float* std_host3, float* lut, void* stream);

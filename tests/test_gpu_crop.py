@@ -218,3 +218,43 @@ def test_long_roi_lists_are_split_into_launches(monkeypatch):
     for r in (0, 7, 12):
         want = ocrop.crop_tensor_ref(imgs[0], rois[r, 1:], target_size=96)
         assert np.array_equal(out[r].cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize('T,swap', [(224, True), (256, False), (96, True)])
+def test_bf16_channels_last_variant_equals_rounded_float_tensor(T, swap):
+    """bpc_roi_crop_bf16 (the pose head's input, process_pose.py:210-212): every value of the float32 tensor rounded to
+    bfloat16 (round-to-nearest-even, what torch's .to(bfloat16) does), stored channels-last -- all regimes and classes,
+    a rejected box included; bit-equal to the float path's output after that rounding."""
+    from bpc_baseline_b200 import batched, synth
+    images = to_dev(synth.make_images(3, seed=9))
+    rng = np.random.default_rng([77, T])
+    R = 256
+    w = rng.integers(8, 1500, R); h = rng.integers(8, 1200, R)
+    w[:8] = [T, 2 * T, 3 * T, 40, 5 * T, 6 * T, 100, 17]; h[:8] = [T, T, 3 * T, 90, 2 * T, 6 * T, 100, 1100]
+    x1 = (rng.random(R) * (synth.IMG_W - w)).astype(np.int64); y1 = (rng.random(R) * (synth.IMG_H - h)).astype(np.int64)
+    rois = np.stack([rng.integers(0, 3, R), x1, y1, x1 + w, y1 + h], axis=1).astype(np.int32)
+    rois[9] = [0, 10, 10, 10, 50]                                   # empty box -> rejected -> all fill
+    drois = to_dev(rois)
+    st_f = torch.zeros(R, dtype=torch.int32, device='cuda'); st_b = torch.zeros_like(st_f)
+    f32 = batched.roi_crop(images, drois, T=T, swap_rb=swap, status=st_f)
+    b16 = batched.roi_crop_bf16(images, drois, T=T, swap_rb=swap, status=st_b)
+    assert b16.dtype == torch.bfloat16 and tuple(b16.shape) == (R, 3, T, T) and b16.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(st_f, st_b) and int(st_b[9]) == 1 and int(st_b.sum()) == 1
+    want = f32.to(torch.bfloat16)
+    assert torch.equal(b16.view(torch.int16), want.contiguous(memory_format=torch.channels_last).view(torch.int16))
+    # device-side ROI count: rows beyond it are left untouched
+    sentinel = torch.full((R, 3, T, T), 7.0, dtype=torch.bfloat16, device='cuda').contiguous(memory_format=torch.channels_last)
+    nro = torch.tensor([100], dtype=torch.int32, device='cuda')
+    batched.roi_crop_bf16(images, drois, T=T, swap_rb=swap, n_rois=nro, out=sentinel)
+    assert torch.equal(sentinel[:100].view(torch.int16), b16[:100].view(torch.int16)) and bool((sentinel[100:] == 7.0).all())
+
+
+def test_bf16_variant_refuses_unaligned_pools():
+    """The bfloat16 output exists on the 2-D TMA path only (include/bpc_b200.h): an image pitch that is not a multiple of 16
+    bytes is an error, never a silent fallback."""
+    from bpc_baseline_b200 import batched
+    images = torch.zeros((1, 600, 601, 3), dtype=torch.uint8, device='cuda')
+    rois = to_dev(np.array([[0, 5, 5, 300, 200]], np.int32))
+    with pytest.raises(RuntimeError):
+        batched.roi_crop_bf16(images, rois, T=224)
+    assert tuple(batched.roi_crop(images, rois, T=224).shape) == (1, 3, 224, 224)

@@ -188,3 +188,56 @@ def test_install_rebinds_reference_modules(golden_scenes):
         pkg.uninstall()
         for n in names:
             sys.modules.pop(n, None)
+
+
+def test_load_scene_batch_equals_capture_from_dir(tmp_path):
+    """f4: the batched BOP loader's device tensors are bit-equal to Capture.from_dir / load_camera_params per scene
+    (reference data_utils.py:399-409, camera_utils.py:6-20), PNG and JPEG files, and feed the matcher directly."""
+    import json
+    import os
+    import cv2
+    import torch
+    from bpc_baseline_b200 import batched, synth
+    from bpc_baseline_b200.utils.data_utils import Capture, load_scene_batch
+    cams = ['cam1', 'cam2', 'cam3']
+    rng = np.random.default_rng(11)
+    dirs = []
+    for sd, ext in (('a', 'png'), ('b', 'jpg')):
+        d = os.path.join(str(tmp_path), sd)
+        os.makedirs(d)
+        dirs.append(d)
+        batch = synth.make_scenes(2, 6, seed=5 + len(dirs))
+        for c, cid in enumerate(cams):
+            per_image = {}
+            for i in (0, 3):
+                K, RT = batch.Ks[i // 3, c], batch.RTs[i // 3, c]
+                per_image[str(i)] = {'cam_K': [float(v) for v in K.ravel()], 'cam_R_w2c': [float(v) for v in RT[:3, :3].ravel()],
+                                     'cam_t_w2c': [float(v) for v in RT[:3, 3]]}
+            with open(os.path.join(d, f'scene_camera_{cid}.json'), 'w') as fh:
+                json.dump(per_image, fh)
+            os.makedirs(os.path.join(d, f'rgb_{cid}'))
+            for i in (0, 3):
+                yy, xx = np.mgrid[0:40, 0:56]
+                img = np.stack([xx + yy + 5 * c + 20 * k for k in range(3)], axis=2).astype(np.uint8) if ext == 'jpg' \
+                    else rng.integers(0, 256, (40, 56, 3), dtype=np.uint8)       # JPEG: smooth ramps (decoders agree closely on those)
+                cv2.imwrite(os.path.join(d, f'rgb_{cid}', f'{i:06d}.{ext}'), img)
+    scene_dirs, image_ids = [dirs[0], dirs[0], dirs[1], dirs[1]], [0, 3, 3, 0]
+    sb = load_scene_batch(scene_dirs, cams, image_ids)
+    assert sb.Ks.is_cuda and sb.Ks.dtype == torch.float32 and tuple(sb.Ks.shape) == (4, 3, 3, 3)
+    assert sb.RTs.dtype == torch.float64 and tuple(sb.RTs.shape) == (4, 3, 4, 4)
+    assert sb.images.dtype == torch.uint8 and tuple(sb.images.shape) == (12, 40, 56, 3) and set(sb.decoders) == {'cv2+pinned'}
+    for s, (d, i) in enumerate(zip(scene_dirs, image_ids)):
+        cap = Capture.from_dir(d, cams, i, 8)
+        assert np.array_equal(sb.Ks[s].cpu().numpy(), np.stack(cap.Ks))
+        assert np.array_equal(sb.RTs[s].cpu().numpy(), np.stack(cap.RTs))
+        assert np.array_equal(sb.images[3 * s:3 * s + 3].cpu().numpy(), np.stack(cap.images))
+        got = sb.capture(s, 8)
+        assert all(np.array_equal(a, b) for a, b in zip(got.images, cap.images)) and got.RTs[1].dtype == np.float64
+    # the tensors are the batched API's input layout
+    F = batched.fundamental(sb.Ks, sb.RTs)
+    assert tuple(F.shape) == (4, 3, 3, 3) and bool(torch.isfinite(F).all())
+    # nvJPEG path: same shapes, pixels close to cv2's (not bit-identical by design: a different JPEG decoder)
+    sj = load_scene_batch(scene_dirs[2:], cams, image_ids[2:], decode='nvjpeg')
+    assert set(sj.decoders) == {'nvjpeg'} and tuple(sj.images.shape) == (6, 40, 56, 3)
+    diff = (sj.images.int() - sb.images[6:].int()).abs()
+    assert float(diff.float().mean()) < 3.0                              # chroma upsampling / IDCT differ between libjpeg-turbo and nvJPEG

@@ -69,3 +69,45 @@ def test_host_stream_equals_device_path_step_by_step():
     refill(hb, 0)
     out = pipe.run_host()
     assert torch.equal(out['idx'], results[0]['idx'])
+
+
+def test_pose_head_on_the_bf16_chunk_buffer_matches_the_per_crop_float32_loop():
+    """f1: MatchCropPipeline(crop_dtype=bfloat16) -> PoseHeadConsumer (SimplePoseNet in bf16 channels-last, fed the chunk
+    buffer as it stands) against the reference's flow -- float32 crops, the network called once per crop, decode per crop
+    (process_pose.py:210-229).  Tolerance: 3 degrees of geodesic distance between the decoded rotations (bf16 has 8 mantissa
+    bits; a random-init ResNet50 amplifies input rounding more than a trained one)."""
+    import numpy as np
+    from bpc_baseline_b200 import batched, pipeline, synth
+    from bpc_baseline_b200.inference.process_pose import decode_rotations
+    from bpc_baseline_b200.pose.head import PoseHeadConsumer, geodesic_degrees
+    from bpc_baseline_b200.pose.models.simple_pose_net import SimplePoseNet
+    from tests.gpu_util import batch_to_dev, to_dev
+    torch.manual_seed(0)
+    S, D, T = 4, 6, 224
+    batch = synth.make_scenes(S, D, seed=123)
+    images = to_dev(synth.make_images(3, seed=3))
+    Ks, RTs, centers, boxes, counts = batch_to_dev(batch)
+    image_of_scene = to_dev(np.tile(np.arange(3, dtype=np.int32), (S, 1)))
+    model = SimplePoseNet(loss_type='6d', pretrained=False).cuda().eval()
+    ref_model = SimplePoseNet(loss_type='6d', pretrained=False).cuda().eval()
+    ref_model.load_state_dict(model.state_dict())
+    pipe16 = pipeline.MatchCropPipeline(S, D, T=T, chunk_rois=32, crop_dtype=torch.bfloat16)
+    head = PoseHeadConsumer(model, pipe16.cap, sub_batch=16)
+    res, offs = pipe16.run_device(Ks, RTs, centers, counts, boxes, images, image_of_scene, consumer=head)
+    n = int(offs[S].item())
+    assert n > 0 and n % 3 == 0
+    got = head.rotations(n)
+    # the reference flow on the float32 crops: batch 1, float32, decode per crop
+    rois = pipe16.rois[:n]
+    f32 = batched.roi_crop(images, rois, T=T)
+    want = []
+    with torch.no_grad():
+        for r in range(n):
+            raw = ref_model(f32[r:r + 1]).float().cpu()
+            want.append(decode_rotations(raw, '6d')[0])
+    want = torch.tensor(np.stack(want), device='cuda')
+    deg = geodesic_degrees(got, want)
+    assert float(deg.max()) < 3.0, float(deg.max())
+    # and the rotations are rotations
+    eye = torch.eye(3, device='cuda').expand(n, 3, 3)
+    assert float((got @ got.transpose(1, 2) - eye).abs().max()) < 1e-3
