@@ -1095,7 +1095,13 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
 //            is emitted as soon as the slot holding its second source row has landed -- its first row is the previous output
 //            row's first or second row, whose horizontal pass is still in registers.
 constexpr int CTA_ROWS = 8;                  // source rows per ring slot (= one TMA box)
-constexpr int CTA_NSLOT = 4;
+#ifndef BPC_CTA_NSLOT
+#define BPC_CTA_NSLOT 4
+#endif
+#ifndef BPC_CTA_MINB
+#define BPC_CTA_MINB 3
+#endif
+constexpr int CTA_NSLOT = BPC_CTA_NSLOT;
 constexpr int CTA_NMAPS = 25;                // box widths 64, 128, ... 1600 bytes (8-byte elements)
 constexpr int CTA_MAX_T = 256;               // 8 consumer warps
 struct CtaMaps { CUtensorMap m[CTA_NMAPS]; };
@@ -1109,7 +1115,7 @@ __host__ __device__ __forceinline__ int cta_smem_bytes(int T) { return LUT_SMEM 
 __device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
 
 template <bool OUT_U8, int TT, bool SWAP, bool BF16 = false>
-__global__ void __launch_bounds__(288, 3)
+__global__ void __launch_bounds__(BPC_CTA_MINB == 4 ? 256 : 288, BPC_CTA_MINB)
 bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom,
                     const float4* __restrict__ xdesc, const float4* __restrict__ ydesc, const int32_t* __restrict__ list1,
                     int32_t* __restrict__ counters, int Trt, uchar4 fill, int swap_rb, const float* __restrict__ lut_g,

@@ -1,5 +1,10 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep: key metrics per kernel + executed-instruction mix by opcode (reads `ncu -i`)."""
+"""Summarise an .ncu-rep: key metrics per kernel + executed-instruction mix by opcode (reads `ncu -i`).
+
+    python tools/ncu_summary.py REP                       # text summary
+    python tools/ncu_summary.py REP --traffic KEY         # also record dram read + write bytes of the first kernel of the report in
+                                                          # profiles/crop_traffic.json under KEY (bench.py's roofline.traffic reads it)
+"""
 import collections, csv, io, subprocess, sys
 
 WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
@@ -20,8 +25,24 @@ def run(args):
 
 def main():
     rep = sys.argv[1]
+    traffic_key = sys.argv[sys.argv.index('--traffic') + 1] if '--traffic' in sys.argv else None
     rows = list(csv.reader(io.StringIO(run([rep, '--page', 'raw', '--csv']))))
     hdr, units = rows[0], rows[1]
+    if traffic_key and len(rows) > 2:
+        import json, os
+        r = rows[2]
+        def gb(name):
+            v, u = float(r[hdr.index(name)]), units[hdr.index(name)]
+            return v * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[u]
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'profiles', 'crop_traffic.json')
+        try:
+            db = json.load(open(path))
+        except Exception:
+            db = {}
+        db[traffic_key] = {'dram_bytes': gb('dram__bytes_read.sum') + gb('dram__bytes_write.sum'), 'dram_read_bytes': gb('dram__bytes_read.sum'),
+                           'dram_write_bytes': gb('dram__bytes_write.sum'), 'kernel': r[hdr.index('Kernel Name')][:80],
+                           'source': f'ncu --set full capture {os.path.basename(rep)} (one launch)'}
+        json.dump(db, open(path, 'w'), indent=1)
     for r in rows[2:]:
         print('===', r[hdr.index('Kernel Name')][:70])
         for w in WANT:
