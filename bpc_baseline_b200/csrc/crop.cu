@@ -554,15 +554,21 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, unsigned long long src, u
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+#ifndef BPC_MBAR_HINT_NS
+#define BPC_MBAR_HINT_NS 2000
+#endif
+// try_wait with a suspend-time hint: a waiting warp sleeps in hardware until the phase completes (or the hint elapses) instead of
+// spinning through try_wait / yield / branch -- spinning consumer and producer warps executed 30 % of the CTA kernel's
+// instructions before the hint was added
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     asm volatile("{\n"
                  ".reg .pred p;\n"
                  "BPC_WAIT:\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
                  "@p bra BPC_DONE;\n"
                  "bra BPC_WAIT;\n"
                  "BPC_DONE:\n"
-                 "}" :: "r"(bar), "r"(parity) : "memory");
+                 "}" :: "r"(bar), "r"(parity), "r"((unsigned)BPC_MBAR_HINT_NS) : "memory");
 }
 
 // Stage rows [s_lo, s_lo + count) of a strip into a warp buffer.  Normal case: one TMA bulk copy of `pitch` bytes
@@ -1112,6 +1118,11 @@ __host__ __device__ __forceinline__ int cta_pitch(int mis0, int w, int cls) { re
 __host__ __device__ __forceinline__ int cta_desc_bytes(int T) { return ydesc_stride(T) * 16; }
 __host__ __device__ __forceinline__ int cta_smem_bytes(int T) { return LUT_SMEM + CTA_NSLOT * CTA_ROWS * cta_pitch_max(T) + 2 * cta_desc_bytes(T) + 256; }
 
+// Lockstep of a crop's strips (a named barrier over the consumer warps): the seven 128-byte pieces of an output row then reach
+// L2 within a short window and are written back together -- DRAM sees whole rows instead of scattered lines (measured on
+// stores alone: 5.7 -> 7.2 TB/s; on the 60-400 px mix 0.79 -> 0.83 of roofline).  Class 1 only, once per ring slot: a barrier every
+// eight output rows made class 3 slower (0.64 -> 0.57: many idle strips, latency-bound) and class 4 is issue-bound.
+#define CTA_LOCKSTEP() do { if (cls == 1) asm volatile("bar.sync 1, %0;" :: "r"(NS * 32) : "memory"); } while (0)
 __device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
 
 template <bool OUT_U8, int TT, bool SWAP, bool BF16 = false>
@@ -1263,7 +1274,7 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
             int ydone = 0;
             for (int c = 0; c < nchunks; ++c, ++cg) {
                 const unsigned j = cg % CTA_NSLOT;
-                mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
+                CTA_LOCKSTEP(); mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty_s + 8 * j);
                 int ndone;
@@ -1282,12 +1293,13 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
                         if (n < 32) break;
                     }
                 }
-                if (store_ok)
-                    for (int r = 0; r < ndone; ++r) {
+                for (int r = 0; r < ndone; ++r) {
+                    if (store_ok) {
                         if (OUT_U8) out.pad(roi, dy0 + ydone + r, x);
                         else if (BF16) { optr16[0] = padh0; optr16[1] = padh1; optr16[2] = padh2; optr16 += 3 * T; }
                         else { optr[0] = out.padf[0]; optr[plane] = out.padf[1]; optr[2 * plane] = out.padf[2]; optr += T; }
                     }
+                }
                 ydone += ndone;
             }
             __syncwarp();
@@ -1312,7 +1324,7 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
             int yout = 0;
             for (int c = 0; c < nchunks; ++c, ++cg) {
                 const unsigned j = cg % CTA_NSLOT;
-                mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
+                CTA_LOCKSTEP(); mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
                 const unsigned rbase = ring_s + j * slot_bytes + colc4;
                 const unsigned rec = dsc + 8u * CTA_ROWS * (unsigned)c;
 #pragma unroll
@@ -1409,7 +1421,7 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
                 constexpr int NT = decltype(nt_c)::value;
                 for (int c = 0; c < nchunks; ++c, ++cg) {
                     const unsigned j = cg % CTA_NSLOT;
-                    mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
+                    CTA_LOCKSTEP(); mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
                     const unsigned rbase = ring_s + j * slot_bytes + colc4;
                     const unsigned rec = dsc + 8u * (unsigned)(c * rps);
                     int r = 0;
@@ -1446,7 +1458,7 @@ bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, con
             float4 d = lds_f4(dsc);
             for (int c = 0; c < nchunks; ++c, ++cg) {
                 const unsigned j = cg % CTA_NSLOT;
-                mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
+                CTA_LOCKSTEP(); mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
                 const int last_row = c * CTA_ROWS + CTA_ROWS - 1;
                 const unsigned sbase = ring_s + j * slot_bytes + colc4 - (unsigned)(c * CTA_ROWS * pitch);     // source row r at sbase + r * pitch
                 while (y < new_h) {
