@@ -646,7 +646,7 @@ def main():
             g_rois = pipe.rois[:gchunk]
             outg = None
             for i in range(3):
-                batched.roi_crop_u8(images, g_rois, T=T, out=cg.slot(i))
+                cg.produce(i, lambda slot: batched.roi_crop_u8(images, g_rois, T=T, out=slot))
                 outg = cg.collect(i)
             torch.cuda.synchronize()
             # parity of the gathered crops: rank 0 regenerates the head of every rank's ROI list and crops it directly
@@ -666,7 +666,7 @@ def main():
             g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             g0.record()
             for i in range(args.gather_steps):
-                batched.roi_crop_u8(images, g_rois, T=T, out=cg.slot(i))
+                cg.produce(i, lambda slot: batched.roi_crop_u8(images, g_rois, T=T, out=slot))
                 cg.collect(i)
             g1.record()
             torch.cuda.synchronize()

@@ -192,6 +192,30 @@ class CropGather:
                     if self.rank == self.root else None)
         self.lut = batched.normalise_lut(self.device)
 
+    def produce(self, i: int, fn) -> None:
+        """Run ``fn(slot(i))`` -- the uint8 crop launch of chunk i -- where it overlaps best.  On the producers that is the
+        current stream (they have nothing else to do).  On the root it is a side stream: the root's own production of chunk
+        i + 1 (issue-bound) then runs under the conversion of chunk i (bound by NVLink ingest and HBM writes) instead of in
+        front of it; ``collect(i)`` waits for it, and the slot is not overwritten before the conversion that last read it
+        (chunk i - 2) has finished."""
+        if self.rank != self.root:
+            fn(self.slot(i))
+            return
+        if not hasattr(self, '_side'):
+            self._side = torch.cuda.Stream(device=self.device)
+            self._ev_prod = [torch.cuda.Event(), torch.cuda.Event()]
+            self._ev_conv = [None, None]
+        main = torch.cuda.current_stream(self.device)
+        b = i & 1
+        with torch.cuda.stream(self._side):
+            if self._ev_conv[b] is not None:
+                self._side.wait_event(self._ev_conv[b])            # conversion of chunk i - 2 has read slot(i)
+            else:
+                self._side.wait_stream(main)                       # first use: whatever prepared the inputs
+            fn(self.slot(i))
+            self._ev_prod[b].record(self._side)
+        self._pending = b
+
     def slot(self, i: int) -> torch.Tensor:
         """This rank's uint8 [chunk_rois,T,T,3] buffer for chunk i."""
         views = self._slots[i & 1]
@@ -201,12 +225,17 @@ class CropGather:
         counts = [self.chunk] * self.world if counts is None else [int(c) for c in counts]
         if len(counts) != self.world or any(not 0 <= c <= self.chunk for c in counts):
             raise ValueError('counts must hold one value in [0, chunk_rois] per rank')
+        def wait_own():                                                # the root's own chunk was produced on the side stream
+            if getattr(self, '_pending', None) is not None:
+                torch.cuda.current_stream(self.device).wait_event(self._ev_prod[self._pending])
         if self.transport == 'p2p':
             dist.all_reduce(self._flag, group=self.group)              # stream-ordered rendezvous, 4 bytes
             if self.rank != self.root:
                 return None
+            wait_own()
             srcs = [self._slots[i & 1][r][:counts[r]] for r in range(self.world)]
         else:
+            wait_own()
             mine = self.slot(i)
             if self.rank == self.root:
                 dist.gather(mine, list(self._staging.unbind(0)), dst=self.root, group=self.group)
@@ -214,8 +243,14 @@ class CropGather:
             else:
                 dist.gather(mine, None, dst=self.root, group=self.group)
                 return None
-        return self._batched.crops_normalise(srcs, self.T, swap_rb=self.swap_rb, lut=self.lut, out=self.out,
-                                             device=self.device)[:sum(counts)]
+        res = self._batched.crops_normalise(srcs, self.T, swap_rb=self.swap_rb, lut=self.lut, out=self.out,
+                                            device=self.device)[:sum(counts)]
+        if getattr(self, '_pending', None) is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._ev_conv[self._pending] = ev
+            self._pending = None
+        return res
 
     def wire_bytes(self, counts=None) -> int:
         """Bytes that cross NVLink into the root for one chunk (the root's own crops do not travel)."""

@@ -61,7 +61,7 @@ def main():
         ok = True
         for i, first in enumerate(range(0, n_check, ck)):
             r = min(ck, n_check - first)
-            batched.roi_crop_u8(images, mine[first:first + r], T=T, out=cg.slot(i))
+            cg.produce(i, lambda slot: batched.roi_crop_u8(images, mine[first:first + r], T=T, out=slot))
             got = cg.collect(i, [r] * world)
             if rank == 0:
                 for src in range(world):
@@ -83,28 +83,30 @@ def main():
     if a.bench:
         rois = torch.as_tensor(rank_rois(rank, chunk, B, H, W)).to(dev)
         res = {}
-        for name, produce in (('produce_and_gather', True), ('gather_only', False)):
+        for name, produce in (('produce_and_gather', True), ('gather_only', False), ('remote_only', False)):
             for b in range(2):                                         # both slots hold valid crops
                 batched.roi_crop_u8(images, rois, T=T, out=cg.slot(b))
             for i in range(3):
                 if produce:
-                    batched.roi_crop_u8(images, rois, T=T, out=cg.slot(i))
+                    cg.produce(i, lambda slot: batched.roi_crop_u8(images, rois, T=T, out=slot))
                 cg.collect(i)
             torch.cuda.synchronize(); dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
+            cnt = [0 if r == 0 else chunk for r in range(world)] if name == 'remote_only' else None     # only crops that cross NVLink
             for i in range(a.steps):
                 if produce:
-                    batched.roi_crop_u8(images, rois, T=T, out=cg.slot(i))
-                cg.collect(i)
+                    cg.produce(i, lambda slot: batched.roi_crop_u8(images, rois, T=T, out=slot))
+                cg.collect(i, cnt)
             e1.record()
             torch.cuda.synchronize()
             ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
             sec = float(ms.item()) * 1e-3 / a.steps
-            res[name] = {'ms_per_chunk': sec * 1e3, 'crops_per_s': world * chunk / sec,
+            ncrops = (world - 1) * chunk if name == 'remote_only' else world * chunk
+            res[name] = {'ms_per_chunk': sec * 1e3, 'crops_per_s': ncrops / sec,
                          'nvlink_ingest_GBps': cg.wire_bytes() / sec / 1e9,
-                         'root_hbm_write_GBps': world * chunk * 3 * T * T * 4 / sec / 1e9}
+                         'root_hbm_write_GBps': ncrops * 3 * T * T * 4 / sec / 1e9}
         if rank == 0:
             print(json.dumps({'what': 'crop gather to rank 0', 'transport': a.transport,
                               'peer_mapping': cg.peers.method if cg.peers else None, 'n_gpus': world,
