@@ -54,8 +54,10 @@ def test_tensor_vs_reference_calls(golden_crops, T, swap):
         assert np.array_equal(out[r].view(np.uint32), want.view(np.uint32)), tuple(b)
 
 
-def test_random_boxes_all_regimes_full_res():
-    """Full-resolution image pool, random boxes U{8..900}, T=224: bit-exact uint8 vs cv2 through the oracle."""
+@pytest.mark.parametrize('T', [224, 256, 160])
+def test_random_boxes_all_regimes_full_res(T):
+    """Full-resolution image pool, random boxes U{8..900}: bit-exact uint8 vs cv2 through the oracle (T = 224 / 256: the
+    compile-time instantiations of the CTA kernel, 160: its run-time-T one with five consumer warps)."""
     from bpc_baseline_b200 import batched, synth
     from oracle.area_spec import regime
     imgs = synth.make_images(2, seed=5, width=1920, height=1080)
@@ -67,23 +69,27 @@ def test_random_boxes_all_regimes_full_res():
         rois.append((int(rng.integers(0, 2)), x1, y1, x1 + int(w), y1 + int(h)))
     # bottom-right corner of the LAST image of the pool: the staging code must not read past the allocation
     rois += [(1, 1700, 900, 1920, 1080), (1, 1500, 700, 1920, 1080), (1, 1000, 300, 1920, 1080), (1, 1912, 1000, 1920, 1080)]
-    rois += [(1, 0, 0, 1920, 1080), (0, 1919 - 8, 1080 - 9, 1919, 1080), (1, 0, 0, 448, 448), (0, 5, 5, 5 + 672, 5 + 448),
-             (0, 0, 0, 224, 224), (1, 100, 100, 100 + 224, 100 + 112)]
+    rois += [(1, 0, 0, 1920, 1080), (0, 1919 - 8, 1080 - 9, 1919, 1080), (1, 0, 0, 2 * T, 2 * T), (0, 5, 5, 5 + 3 * T, 5 + 2 * T),
+             (0, 0, 0, T, T), (1, 100, 100, 100 + T, 100 + T // 2)]                 # integer ratios (regime 2) and scale exactly 1
     rois = np.asarray(rois, np.int32)
-    out = batched.roi_crop_u8(to_dev(imgs), to_dev(rois), T=224).cpu().numpy()
+    out = batched.roi_crop_u8(to_dev(imgs), to_dev(rois), T=T).cpu().numpy()
+    outf = batched.roi_crop(to_dev(imgs), to_dev(rois), T=T, swap_rb=True).cpu().numpy()
+    lut = batched.normalise_lut('cuda').cpu().numpy()
     seen = set()
     for r, (b, x1, y1, x2, y2) in enumerate(rois):
-        want = ocrop.crop_u8_ref(imgs[b], (x1, y1, x2, y2), 224)
-        _, nw, nh, _, _ = ocrop.letterbox_geometry(y2 - y1, x2 - x1, 224)
+        want = ocrop.crop_u8_ref(imgs[b], (x1, y1, x2, y2), T)
+        _, nw, nh, _, _ = ocrop.letterbox_geometry(y2 - y1, x2 - x1, T)
         seen.add(regime(x2 - x1, y2 - y1, nw, nh))
         assert np.array_equal(out[r], want), (r, tuple(rois[r]))
+        assert np.array_equal(outf[r], np.stack([lut[p][want[..., 2 - p]] for p in range(3)])), (r, tuple(rois[r]))
     assert seen == {1, 2, 3}
 
 
-@pytest.mark.parametrize('T,width', [(224, 1920), (64, 1920), (256, 1918), (100, 1913)])
+@pytest.mark.parametrize('T,width', [(224, 1920), (64, 1920), (256, 1920), (128, 3840), (256, 1918), (100, 1913)])
 def test_large_boxes_four_to_six_taps(T, width):
-    """Boxes of 2T .. 5.3T: the 4 / 5 / 6-tap class of the warp kernel (row-streaming ring) and, beyond scale 5, the generic
-    kernel.  width 1920: image pitch a multiple of 16 bytes (2-D TMA staging); 1918 / 1913: the 1-D bulk-copy path."""
+    """Boxes of 2T .. 5.3T: the 4 / 5 / 6-tap class (source-row records in the CTA kernel, wide rows by 1-D bulk copies; the
+    row-streaming ring of the per-strip kernel for unaligned pitches) and, beyond scale 5, the generic kernel.  width 1920 / 3840:
+    image pitch a multiple of 16 bytes (CTA kernel, 2-D TMA staging); 1918 / 1913: the per-strip kernel's 1-D bulk-copy path."""
     from bpc_baseline_b200 import batched, synth
     imgs = synth.make_images(2, seed=9, width=width, height=1080)
     rng = np.random.default_rng([23, T, width])
