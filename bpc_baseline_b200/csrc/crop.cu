@@ -134,6 +134,14 @@ __device__ __forceinline__ void area_taps(int d, double scale, int ssize, int& s
     }
 }
 
+// index of the last source tap of destination index d: start + n - 1 of area_taps() = sx2 - 1 + (the last-tap test), without
+// the weights (no divisions)
+__device__ __forceinline__ int area_last_tap(int d, double scale, int ssize) {
+    const double fsx2 = dadd(dmul((double)d, scale), scale);
+    const int sx2 = min((int)floor(fsx2), ssize - 1);
+    return sx2 - 1 + (dsub(fsx2, (double)sx2) > 1e-3 ? 1 : 0);
+}
+
 // the same taps as a start index and three weights (absent taps = +0.0f); valid when n <= 3 (scale < 2)
 __device__ __forceinline__ void area_taps3(int d, double scale, int ssize, int& start, int& n, float& w0, float& w1, float& w2) {
     float af, am, al;
@@ -176,10 +184,9 @@ __device__ void src_row_records(float2* ysrc, int cap, const RoiGeom& g, int max
     for (int s = tid; s < hpad; s += 256) ysrc[s] = make_float2(0.f, 0.f);
     __syncthreads();
     for (int d = tid; d < g.new_h && !*bad; d += 256) {
-        int ys, yn, fl, pys = 0, pyn = 0, pfl; float bf, bm, bl, pf, pm, pl;
+        int ys, yn, fl; float bf, bm, bl;
         area_taps(d, g.scale_y, g.h, ys, yn, bf, bm, bl, fl);
-        if (d > 0) area_taps(d - 1, g.scale_y, g.h, pys, pyn, pf, pm, pl, pfl);
-        const int prev_last = d > 0 ? pys + pyn - 1 : -1;
+        const int prev_last = d > 0 ? area_last_tap(d - 1, g.scale_y, g.h) : -1;
         if (yn < 1 || yn > maxtaps || ys < prev_last || ys + yn > g.h) { *bad = 1; break; }
         for (int t = 0; t < yn; ++t) {
             const int s = ys + t;
