@@ -1108,13 +1108,10 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
 //            is emitted as soon as the slot holding its second source row has landed -- its first row is the previous output
 //            row's first or second row, whose horizontal pass is still in registers.
 constexpr int CTA_ROWS = 8;                  // source rows per ring slot (= one TMA box)
-#ifndef BPC_CTA_NSLOT
-#define BPC_CTA_NSLOT 4
-#endif
-#ifndef BPC_CTA_MINB
-#define BPC_CTA_MINB 3
-#endif
-constexpr int CTA_NSLOT = BPC_CTA_NSLOT;
+// ring slots and resident CTAs per SM: the T = 224 float instantiation (the benchmark's) runs 4 CTAs/SM (8 warps, 63 registers,
+// three slots: 55 KB of shared memory), which buys classes 3 and 4 latency hiding (0.66 -> 0.70, 0.67 -> 0.69) and leaves class 1
+// where it was; the run-time-T and T = 256 instantiations (up to 9 warps) keep four slots and 3 CTAs/SM
+__host__ __device__ constexpr int cta_nslot(int TT) { return TT == 224 ? 3 : 4; }
 constexpr int CTA_NMAPS = 25;                // box widths 64, 128, ... 1600 bytes (8-byte elements)
 constexpr int CTA_MAX_T = 256;               // 8 consumer warps
 struct CtaMaps { CUtensorMap m[CTA_NMAPS]; };
@@ -1123,7 +1120,7 @@ __host__ __device__ __forceinline__ int cta_pitch_max(int T) { return ((15 + 3 *
 // (class 1: three words from the aligned tap address; class 4: up to six taps padded to the warp maximum)
 __host__ __device__ __forceinline__ int cta_pitch(int mis0, int w, int cls) { return ((mis0 + 3 * w + (cls == 4 ? 40 : 12) + 63) >> 6) << 6; }
 __host__ __device__ __forceinline__ int cta_desc_bytes(int T) { return ydesc_stride(T) * 16; }
-__host__ __device__ __forceinline__ int cta_smem_bytes(int T) { return LUT_SMEM + CTA_NSLOT * CTA_ROWS * cta_pitch_max(T) + 2 * cta_desc_bytes(T) + 256; }
+__host__ __device__ __forceinline__ int cta_smem_bytes(int T, int nslot) { return LUT_SMEM + nslot * CTA_ROWS * cta_pitch_max(T) + 2 * cta_desc_bytes(T) + 256; }
 
 // Lockstep of a crop's strips (a named barrier over the consumer warps): the seven 128-byte pieces of an output row then reach
 // L2 within a short window and are written back together -- DRAM sees whole rows instead of scattered lines (measured on
@@ -1133,12 +1130,13 @@ __host__ __device__ __forceinline__ int cta_smem_bytes(int T) { return LUT_SMEM 
 __device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
 
 template <bool OUT_U8, int TT, bool SWAP, bool BF16 = false>
-__global__ void __launch_bounds__(BPC_CTA_MINB == 4 ? 256 : 288, BPC_CTA_MINB)
+__global__ void __launch_bounds__(TT == 224 ? 256 : 288, TT == 224 ? 4 : 3)
 bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom,
                     const float4* __restrict__ xdesc, const float4* __restrict__ ydesc, const int32_t* __restrict__ list1,
                     int32_t* __restrict__ counters, int Trt, uchar4 fill, int swap_rb, const float* __restrict__ lut_g,
                     float* __restrict__ outf, uint8_t* __restrict__ outb, const __grid_constant__ CtaMaps tm) {
     extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int CTA_NSLOT = cta_nslot(TT);
     float* lut = reinterpret_cast<float*>(smem);
     const int T = TT ? TT : Trt;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1866,8 +1864,9 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
         else if (T == 224) fn = sw ? bpc_crop_cta_kernel<OUT_U8, 224, true> : bpc_crop_cta_kernel<OUT_U8, 224, false>;
         else if (T == 256) fn = sw ? bpc_crop_cta_kernel<OUT_U8, 256, true> : bpc_crop_cta_kernel<OUT_U8, 256, false>;
         else fn = sw ? bpc_crop_cta_kernel<OUT_U8, 0, true> : bpc_crop_cta_kernel<OUT_U8, 0, false>;
-        const int smem_bytes = cta_smem_bytes(T);
-        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cta_smem_bytes(CTA_MAX_T));
+        const int nslot = cta_nslot((!OUT_U8 && !BF16 && T == 224) ? 224 : 0);      // as the instantiation picked above
+        const int smem_bytes = cta_smem_bytes(T, nslot);
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cta_smem_bytes(T == 224 ? 224 : CTA_MAX_T, nslot));
         if (e != cudaSuccess) return (int)e;
         const int threads = 32 * ((T + 31) / 32 + 1);
         int dev = 0, sms = 148, per_sm = 3;
