@@ -295,6 +295,9 @@ __device__ void match_carve(MatchSmem& ms, unsigned char* p, int Dmax, int nwarp
 // ------------------------------------------------------------------------------------------------------
 // PoseEstimator._match for one scene per CTA
 // ------------------------------------------------------------------------------------------------------
+// SPILL = false: the scene's state is carved out of shared memory (the compiler then addresses it with LDS / STS, not generic
+// loads); SPILL = true: a per-CTA block of the caller's workspace (Dmax beyond ~550)
+template <bool SPILL>
 __global__ void __launch_bounds__(256, 2) bpc_match_kernel(const float* __restrict__ Ks, const double* __restrict__ RTs,
                                  const double* __restrict__ centers, const int32_t* __restrict__ counts,
                                  int S, int Dmax, float threshold,
@@ -305,7 +308,8 @@ __global__ void __launch_bounds__(256, 2) bpc_match_kernel(const float* __restri
     const int tid = threadIdx.x, nth = blockDim.x, nwarps = nth >> 5;
     MatchSmem ms;
     // scenes too large for shared memory (Dmax > ~450) keep their state in the caller's workspace, one block per CTA
-    match_carve(ms, spill != nullptr ? spill + (size_t)blockIdx.x * spill_per_cta : smem_raw, Dmax, nwarps);
+    if (SPILL) match_carve(ms, spill + (size_t)blockIdx.x * spill_per_cta, Dmax, nwarps);
+    else match_carve(ms, smem_raw, Dmax, nwarps);
     const double NaN = __longlong_as_double(0x7ff8000000000000LL);
 
     for (int s = blockIdx.x; s < S; s += gridDim.x) {
@@ -881,10 +885,11 @@ extern "C" int bpc_match_triangulate(const float* Ks, const double* RTs, const d
         if (!workspace || ((uintptr_t)workspace & 15) != 0) return workspace ? BPC_EALIGN : BPC_EWORKSPACE;
         if (workspace_bytes < spill * (size_t)grid) return BPC_EWORKSPACE;
     }
-    cudaError_t e = cudaFuncSetAttribute(bpc_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MATCH_MAX_SMEM);
+    auto kern = spill ? bpc_match_kernel<true> : bpc_match_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MATCH_MAX_SMEM);
     if (e != cudaSuccess) return (int)e;
-    bpc_match_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(Ks, RTs, centers, counts, S, Dmax, threshold, idx, n, cost, X, reproj, F,
-                                                                    spill ? (unsigned char*)workspace : nullptr, spill);
+    kern<<<grid, threads, smem, (cudaStream_t)stream>>>(Ks, RTs, centers, counts, S, Dmax, threshold, idx, n, cost, X, reproj, F,
+                                                        spill ? (unsigned char*)workspace : nullptr, spill);
     BPC_LAUNCH_CHECK();
     const long long slots = (long long)S * Dmax;
     bpc_match_tri_kernel<<<(unsigned)((slots + 127) / 128), 128, 0, (cudaStream_t)stream>>>(Ks, RTs, centers, idx, n, S, Dmax, X, reproj);
