@@ -227,6 +227,8 @@ def reprojection_error(P: torch.Tensor, X: torch.Tensor, pts: torch.Tensor) -> t
     """Per-view pixel error f64 [n,3] (utils/triangulation.py:14-18)."""
     _chk(P, torch.float64, 'P', 4); _chk(X, torch.float64, 'X', 2); _chk(pts, torch.float64, 'pts', 3)
     n = P.shape[0]
+    if tuple(P.shape) != (n, 3, 3, 4) or tuple(X.shape) != (n, 3) or tuple(pts.shape) != (n, 3, 2):
+        raise RuntimeError('expected P [n,3,3,4], X [n,3] and pts [n,3,2]')
     err = torch.empty((n, 3), dtype=torch.float64, device=P.device)
     with torch.cuda.device(P.device):
         _lib.check(_lib.load().bpc_reprojection_error(_p(P), _p(X), _p(pts), n, _p(err), _stream(P.device)), 'bpc_reprojection_error')
@@ -294,6 +296,10 @@ def build_rois(boxes: torch.Tensor, idx: torch.Tensor, n: torch.Tensor, image_of
     dev = boxes.device
     if rois is None:
         rois = torch.empty((S * K * 3, 5), dtype=torch.int32, device=dev)
+    else:
+        _chk(rois, torch.int32, 'rois', 2)
+        if rois.shape[0] < S * K * 3 or rois.shape[1] != 5:
+            raise RuntimeError('rois must be int32 [>= S*Kmax*3, 5]')
     offs = torch.empty((S + 1,), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().bpc_build_rois(_p(boxes), _p(idx), _p(n), _p(image_of_scene), S, D, K, _p(offs), _p(rois),
@@ -321,6 +327,7 @@ def normalise_lut(device, mean: Sequence[float] = MEAN, std: Sequence[float] = S
 _WS_CACHE: dict = {}
 MAX_ROIS_PER_LAUNCH = 32768
 MAX_TARGET = 1024              # BPC_MAX_TARGET
+MAX_ROI_WIDTH = 8192           # BPC_MAX_ROI_WIDTH
 
 
 def _crop_workspace(dev, R: int, T: int) -> torch.Tensor:
@@ -334,6 +341,13 @@ def _crop_workspace(dev, R: int, T: int) -> torch.Tensor:
         ws = torch.empty((max(need, 1 << 16),), dtype=torch.uint8, device=dev)
         _WS_CACHE[key] = ws
     return ws
+
+
+def _chk_status(status, R: int) -> None:
+    if status is not None:
+        _chk(status, torch.int32, 'status', 1)
+        if status.shape[0] < R:
+            raise RuntimeError('status must hold one int32 per ROI')
 
 
 def _crop_args(images, rois, T, fill):
@@ -367,8 +381,7 @@ def roi_crop(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(255, 
         _chk(out, torch.float32, 'out', 4)
         if out.shape[0] < R or tuple(out.shape[1:]) != (3, T, T):
             raise RuntimeError('out must be [>=R,3,T,T]')
-    if status is not None:
-        _chk(status, torch.int32, 'status', 1)
+    _chk_status(status, R)
     if n_rois is not None:
         _chk(n_rois, torch.int32, 'n_rois')
     ws = _crop_workspace(dev, min(R, MAX_ROIS_PER_LAUNCH), T)
@@ -400,8 +413,7 @@ def roi_crop_bf16(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(
         if out.dtype != torch.bfloat16 or not out.is_cuda or out.dim() != 4 or out.shape[0] < R or tuple(out.shape[1:]) != (3, T, T) \
                 or not out.is_contiguous(memory_format=torch.channels_last):
             raise RuntimeError('out must be a channels_last bfloat16 CUDA tensor [>=R,3,T,T]')
-    if status is not None:
-        _chk(status, torch.int32, 'status', 1)
+    _chk_status(status, R)
     if n_rois is not None:
         _chk(n_rois, torch.int32, 'n_rois')
     ws = _crop_workspace(dev, min(R, MAX_ROIS_PER_LAUNCH), T)
@@ -423,8 +435,13 @@ def roi_crop_u8(images: torch.Tensor, rois: torch.Tensor, T: int = 256, fill=(25
     dev = images.device
     if out is None:
         out = torch.empty((R, T, T, 3), dtype=torch.uint8, device=dev)
-    if status is not None:
-        _chk(status, torch.int32, 'status', 1)
+    else:
+        _chk(out, torch.uint8, 'out', 4)
+        if out.shape[0] < R or tuple(out.shape[1:]) != (T, T, 3):
+            raise RuntimeError('out must be uint8 [>=R,T,T,3]')
+    _chk_status(status, R)
+    if n_rois is not None:
+        _chk(n_rois, torch.int32, 'n_rois')
     ws = _crop_workspace(dev, min(R, MAX_ROIS_PER_LAUNCH), T)
     with torch.cuda.device(dev):
         for lo in range(0, R, MAX_ROIS_PER_LAUNCH):

@@ -40,7 +40,11 @@ def letterbox_preserving_aspect_ratio(img, target_size=256, fill_color=(255, 255
         raise NotImplementedError(f'target_size above {batched.MAX_TARGET} is not supported by the CUDA crop kernels')
     images = _host.to_dev(img[None], np.uint8)
     rois = _host.to_dev([[0, 0, 0, w, h]], np.int32)
-    canvas = batched.roi_crop_u8(images, rois, T=int(target_size), fill=fill_color)
+    import torch
+    status = torch.zeros(1, dtype=torch.int32, device=images.device)
+    canvas = batched.roi_crop_u8(images, rois, T=int(target_size), fill=fill_color, status=status)
+    if int(status.item()):                                  # e.g. wider than BPC_MAX_ROI_WIDTH: an error, never a blank canvas
+        raise _resize_error(f'crop of {w} x {h} pixels was rejected by the CUDA crop kernels (wider than {batched.MAX_ROI_WIDTH}?)')
     return _host.to_host(canvas)[0].copy(), scale, dx, dy
 
 
