@@ -7,171 +7,31 @@
 //   regime 2  both shrink, integer ratio : integer box sum; 2x2 -> (sum+2)>>2
 //   regime 3  either axis grows          : 11-bit fixed-point bilinear with area-mode coordinates
 //
-// Three kernels per call:
+// Kernels of one call (shared pieces in crop_common.cuh):
 //   bpc_crop_prep     one CTA per ROI: letterbox geometry (float64, as Python / OpenCV compute it), regime
 //                     and class of the ROI, and -- for the fast classes -- the per-column and per-row tap
-//                     descriptors (start index + three float32 weights, absent taps = +0.0f), so that no
-//                     float64 arithmetic is left in the hot kernel;
-//   bpc_crop_warp     persistent CTAs; the unit of work is (ROI, strip of 32 output columns), taken by ONE
-//                     WARP from a global atomic counter, plus one "padding" item per ROI.  A warp stages the
-//                     ~130-byte source segments its strip needs into its own slice of shared memory with TMA
-//                     (2-D tensor-map boxes of four rows when the image pitch is a multiple of 16 bytes, else one
-//                     1-D bulk copy per row; completion on per-warp mbarriers) and streams down its strip, one
-//                     lane per column: the horizontal pass of a source row is computed once and reused by the
-//                     output rows that tap it.  No CTA barrier, no idle warps behind a narrow letterbox.
-//                     Classes: 1 = regime 1 with scale < 2 on both axes (<= 3 taps per axis, double-buffered
-//                     batches of output rows) and scale exactly 1; 3 = regime 3 (same batches); 4 = regime 1
-//                     with 4..6 taps per axis (2 <= scale <= 5; source rows stream through a four-slot ring);
+//                     descriptors (start index + float32 weights, absent taps = +0.0f; per-SOURCE-row records for
+//                     the area classes), so that no float64 arithmetic is left in the hot kernels; sorts the ROIs
+//                     into the lists of the kernels below;
+//   bpc_crop_cta      (crop_cta.cu) THE hot kernel: one crop per CTA, a producer warp issuing one full-width 2-D TMA
+//                     box of eight source rows per ring slot, consumer warps = 32-column strips.  Classes 1 (regime
+//                     1, scale < 2, <= 3 taps per axis; scale exactly 1), 3 (regime 3) and 4 (regime 1 with 4..6 taps
+//                     per axis, 2 <= scale <= 5) and rejected boxes, whenever the image pitch is a multiple of 16
+//                     bytes and T <= 256;
+//   bpc_crop_warp     round 1's kernel, the path for other pitches / narrow images / T > 256: persistent CTAs, the
+//                     unit of work is (ROI, strip of 32 output columns), taken by ONE WARP from a global atomic
+//                     counter, plus one "padding" item per ROI; per-warp TMA staging (2-D boxes of four / eight rows,
+//                     or one 1-D bulk copy per row); walks its own list and exits at once when that is empty;
 //   bpc_crop_generic  persistent CTAs over the (rare) remaining ROIs (class 2): integer ratios >= 2, scale > 5,
 //                     source rows streamed through shared memory in chunks (boxes as large as the image).
 // The dominant traffic is the float32 output (3*T*T*4 B per ROI): each warp stores 128 contiguous bytes per
 // plane and row; padding rows are written with 16-byte stores.
-#include <cuda.h>
-
-#include <stdlib.h>
-#include <string.h>
-
 #include <mutex>
 #include <type_traits>
 
-#include "common.cuh"
+#include "crop_common.cuh"
 
 namespace bpc {
-
-constexpr int CROP_BAND = 8;                 // generic kernel: output rows per work item
-constexpr int CROP_RAW_BYTES = 40 * 1024;    // generic kernel: staged source bytes
-constexpr int WARP_BUF = 3584;               // warp kernel: bytes of one staging buffer (two per warp)
-constexpr int WARP_DESC = 32 * 16;           // warp kernel: 32 row descriptors (two rings per warp)
-constexpr int WARP_SMEM = 8320;              // 2 staging buffers + 2 descriptor rings + eight mbarriers, padded to a multiple of 128
-static_assert(WARP_SMEM % 128 == 0 && WARP_SMEM >= 2 * WARP_BUF + 2 * WARP_DESC + 64 && WARP_BUF % 128 == 0, "TMA box destinations are 128-byte aligned");
-constexpr int WARPK_WARPS = 8;
-constexpr int LUT_STRIDE = 257;              // shared-memory LUT: 256 entries + the normalised fill value per output channel
-constexpr int LUT_SMEM = 3200;               // 3 * 257 floats, padded to a multiple of 128 (TMA destinations follow)
-constexpr int WARPK_SMEM = WARPK_WARPS * WARP_SMEM + LUT_SMEM;
-constexpr int STREAM_ROWS = 8;               // streaming class-1 path: source rows per ring slot (= one TMA box)
-constexpr int STREAM_MAX_PITCH = 288;        // widest staging pitch of a class-1 strip (32 columns at scale < 2 need <= 256)
-constexpr int YSRC_PAD = 16;                 // per-source-row table: zero entries behind the last row (whole slots run to completion)
-static_assert(LUT_SMEM % 128 == 0 && LUT_SMEM >= 3 * LUT_STRIDE * 4, "LUT block");
-// descriptors per ROI: x axis ds float4, y axis ds + 8 float4 (class 1 reads the y block as 2*ds + 16 float2 source-row records),
-// ds = T rounded up to 32
-__host__ __device__ __forceinline__ int desc_stride(int T) { return (T + 31) & ~31; }
-// float4 records per ROI on the y axis: ds + 8 (class 1 reads the block as 2 ds + 16 float2 source-row records); up to T = 256 the
-// block also holds the source-row records of a class-4 crop for the CTA kernel (h <= 5 T rows + one padded slot + 16)
-__host__ __device__ __forceinline__ int ydesc_stride(int T) {
-    const int base = desc_stride(T) + 8, rows4 = (5 * T + 32 + 1) / 2;
-    return (T <= 256 && rows4 > base) ? rows4 : base;
-}
-
-struct RoiGeom {                             // 88 bytes, workspace
-    double scale_x, scale_y, inv_x, inv_y;
-    unsigned long long src;                  // byte address of (y1, x1) in its image
-    int w, h, new_w, new_h, dx, dy;
-    int regime;                              // 0 rejected, 1 / 2 / 3
-    int cls;                                 // -1 beyond the device count, 0 rejected (all fill), 1 fast area, 3 fast linear, 2 generic
-    int isx, isy;
-    int pitch, pad_;
-};
-static_assert(sizeof(RoiGeom) == 88, "RoiGeom layout");
-
-// 2-D tensor maps over the image pool seen as [B*H rows][W*3/4 uint32] (only when W*3 is a multiple of 16): one map
-// per staging pitch, box = {pitch / 4 words, 4 rows} (2 rows for the two widest), so one TMA instruction stages four
-// source rows of a strip instead of one bulk copy per row; rows / columns beyond the pool are zero-filled by the TMA
-// unit, which removes the guarded tail path.
-#ifndef BPC_L2_PROMO
-#define BPC_L2_PROMO CU_TENSOR_MAP_L2_PROMOTION_L2_128B
-#endif
-constexpr int N_TMAPS = 15;
-constexpr int N_TMAPS8 = 8;                  // 8-row boxes for the streaming class-1 path: pitches 64 .. 288
-struct TmapSet { CUtensorMap m[N_TMAPS]; CUtensorMap m8[N_TMAPS8]; };
-__host__ __device__ __forceinline__ int tmap_pitch(int need) { return need <= 448 ? (need < 64 ? 64 : ((need + 31) & ~31)) : ((need + 63) & ~63); }
-__host__ __device__ __forceinline__ int tmap_index(int pitch) { return pitch <= 448 ? (pitch - 64) / 32 : 13 + (pitch - 512) / 64; }
-__host__ __device__ __forceinline__ int tmap_rows(int pitch) { return pitch <= 448 ? 4 : 2; }
-constexpr int TMAP_MAX_PITCH = 576;
-
-struct YDesc {                               // generic kernel, per output row of the band
-    int start;
-    int n;                                   // taps (regime 1/2) ; regime 3: second source row
-    float bf, bm, bl;                        // regime 1 weights ; regime 3: b0, b1 as int bits
-    int flags;                               // bit0 has_first, bit1 has_last
-};
-
-__device__ __forceinline__ uint4 ld_nc_v4(const void* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// computeResizeAreaTab for one destination index d (OpenCV resize.cpp), all in float64.
-__device__ __forceinline__ void area_taps(int d, double scale, int ssize, int& start, int& n, float& af, float& am, float& al, int& flags) {
-    const double fsx1 = dmul((double)d, scale);
-    const double fsx2 = dadd(fsx1, scale);
-    const double cell = fmin(scale, dsub((double)ssize, fsx1));
-    int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
-    sx2 = min(sx2, ssize - 1);
-    sx1 = min(sx1, sx2);
-    flags = 0;
-    af = 0.f; al = 0.f;
-    am = __double2float_rn(ddiv(1.0, cell));
-    start = sx1;
-    n = sx2 - sx1;
-    if (dsub((double)sx1, fsx1) > 1e-3) {
-        flags |= 1;
-        af = __double2float_rn(ddiv(dsub((double)sx1, fsx1), cell));
-        start = sx1 - 1;
-        ++n;
-    }
-    if (dsub(fsx2, (double)sx2) > 1e-3) {
-        flags |= 2;
-        al = __double2float_rn(ddiv(fmin(fmin(dsub(fsx2, (double)sx2), 1.0), cell), cell));
-        ++n;
-    }
-}
-
-// index of the last source tap of destination index d: start + n - 1 of area_taps() = sx2 - 1 + (the last-tap test), without
-// the weights (no divisions)
-__device__ __forceinline__ int area_last_tap(int d, double scale, int ssize) {
-    const double fsx2 = dadd(dmul((double)d, scale), scale);
-    const int sx2 = min((int)floor(fsx2), ssize - 1);
-    return sx2 - 1 + (dsub(fsx2, (double)sx2) > 1e-3 ? 1 : 0);
-}
-
-// the same taps as a start index and three weights (absent taps = +0.0f); valid when n <= 3 (scale < 2)
-__device__ __forceinline__ void area_taps3(int d, double scale, int ssize, int& start, int& n, float& w0, float& w1, float& w2) {
-    float af, am, al;
-    int flags;
-    area_taps(d, scale, ssize, start, n, af, am, al, flags);
-    float w[3] = {0.f, 0.f, 0.f};
-    int k = 0;
-    if (flags & 1) w[k++] = af;
-    const int m = n - (flags & 1) - ((flags >> 1) & 1);
-    for (int t = 0; t < m && k < 3; ++t) w[k++] = am;
-    if ((flags & 2) && k < 3) w[k++] = al;
-    w0 = w[0]; w1 = w[1]; w2 = w[2];
-}
-
-// area-mode coordinates of the generic linear resize for one destination index d.
-__device__ __forceinline__ void linear_coef(int d, double scale, double inv, int ssize, int& s0, int& w0, int& w1, int& edge) {
-    int s = (int)floor(dmul((double)d, scale));
-    float f = __double2float_rn(dsub((double)(d + 1), dmul((double)(s + 1), inv)));
-    f = (f <= 0.f) ? 0.f : __fsub_rn(f, floorf(f));
-    if (s < 0) { f = 0.f; s = 0; }
-    edge = 0;
-    if (s + 1 >= ssize) {
-        edge = 1;
-        if (s >= ssize - 1) { f = 0.f; s = ssize - 1; }
-    }
-    s0 = s;
-    w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
-    w1 = __float2int_rn(__fmul_rn(f, 2048.f));
-}
-
 
 // Per-SOURCE-row records of an area resize with at most `maxtaps` taps per output row (collective over the 256 threads of a prep
 // CTA): record s = (ba, bb); |ba| = weight of source row s in the output row being accumulated, sign bit of ba set = that output
@@ -338,246 +198,8 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
 }
 
 // ------------------------------------------------------------------------------------------------------
-// shared output helpers
-// ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned short bf16_bits(float v) {       // round-to-nearest-even float32 -> bfloat16
-    unsigned short r;
-    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(v));
-    return r;
-}
-
-// BF16: the float path's values rounded to bfloat16 and stored channels-last ([R][T][T][3], what a bf16 tensor-core network reads)
-template <bool OUT_U8, bool BF16 = false>
-struct Out {
-    float* outf; uint8_t* outb;
-    const float* lut;           // shared memory [3][LUT_STRIDE]
-    int T, swap_rb;
-    uint8_t fillc[3];
-    float padf[3];
-
-    __device__ __forceinline__ void px(int roi, int y, int x, int b0, int b1, int b2) const {   // source channel order
-        if (OUT_U8) {
-            uint8_t* o = outb + (((size_t)roi * T + y) * T + x) * 3;
-            o[0] = (uint8_t)b0; o[1] = (uint8_t)b1; o[2] = (uint8_t)b2;
-        } else {
-            const int s0 = swap_rb ? b2 : b0, s2 = swap_rb ? b0 : b2;
-            if (BF16) {
-                unsigned short* o = reinterpret_cast<unsigned short*>(outf) + (((size_t)roi * T + y) * T + x) * 3;
-                o[0] = bf16_bits(lut[s0]); o[1] = bf16_bits(lut[LUT_STRIDE + b1]); o[2] = bf16_bits(lut[2 * LUT_STRIDE + s2]);
-            } else {
-                float* o = outf + ((size_t)roi * 3 * T + y) * T + x;
-                o[0] = lut[s0];
-                o[(size_t)T * T] = lut[LUT_STRIDE + b1];
-                o[(size_t)2 * T * T] = lut[2 * LUT_STRIDE + s2];
-            }
-        }
-    }
-    __device__ __forceinline__ void pad(int roi, int y, int x) const {
-        if (OUT_U8) {
-            uint8_t* o = outb + (((size_t)roi * T + y) * T + x) * 3;
-            o[0] = fillc[0]; o[1] = fillc[1]; o[2] = fillc[2];
-        } else if (BF16) {
-            unsigned short* o = reinterpret_cast<unsigned short*>(outf) + (((size_t)roi * T + y) * T + x) * 3;
-            o[0] = bf16_bits(padf[0]); o[1] = bf16_bits(padf[1]); o[2] = bf16_bits(padf[2]);
-        } else {
-            float* o = outf + ((size_t)roi * 3 * T + y) * T + x;
-            o[0] = padf[0]; o[(size_t)T * T] = padf[1]; o[(size_t)2 * T * T] = padf[2];
-        }
-    }
-    // rows [ra, rb) of all three planes = fill; collective over nth threads
-    __device__ void pad_rows(int roi, int ra, int rb, int tid, int nth) const {
-        if (rb <= ra) return;
-        if (OUT_U8) {
-            uint8_t* o = outb + ((size_t)roi * T + ra) * T * 3;
-            const int nbytes = (rb - ra) * T * 3;
-            for (int e = tid; e < nbytes; e += nth) o[e] = fillc[e % 3];
-        } else if (BF16) {
-            unsigned short* o = reinterpret_cast<unsigned short*>(outf) + ((size_t)roi * T + ra) * T * 3;
-            const int n = (rb - ra) * T * 3;
-            const unsigned short f0 = bf16_bits(padf[0]), f1 = bf16_bits(padf[1]), f2 = bf16_bits(padf[2]);
-            if ((((size_t)(uintptr_t)o) & 3) == 0 && (n & 1) == 0) {          // 32-bit stores of the period-3 pattern
-                unsigned* o2 = reinterpret_cast<unsigned*>(o);
-                const unsigned p0 = f0 | ((unsigned)f1 << 16), p1 = f2 | ((unsigned)f0 << 16), p2 = f1 | ((unsigned)f2 << 16);
-                for (int e = tid; e < (n >> 1); e += nth) { const int m = e % 3; o2[e] = m == 0 ? p0 : (m == 1 ? p1 : p2); }
-            } else {
-                for (int e = tid; e < n; e += nth) { const int m = e % 3; o[e] = m == 0 ? f0 : (m == 1 ? f1 : f2); }
-            }
-        } else if ((T & 3) == 0) {
-            const int n4 = (rb - ra) * (T >> 2);
-            for (int p = 0; p < 3; ++p) {
-                float4* o = reinterpret_cast<float4*>(outf + ((size_t)(roi * 3 + p) * T + ra) * T);
-                const float4 v = make_float4(padf[p], padf[p], padf[p], padf[p]);
-                for (int e = tid; e < n4; e += nth) o[e] = v;
-            }
-        } else {
-            const int n1 = (rb - ra) * T;
-            for (int p = 0; p < 3; ++p) {
-                float* o = outf + ((size_t)(roi * 3 + p) * T + ra) * T;
-                for (int e = tid; e < n1; e += nth) o[e] = padf[p];
-            }
-        }
-    }
-};
-
-template <bool OUT_U8, bool BF16>
-__device__ __forceinline__ void out_init(Out<OUT_U8, BF16>& o, float* outf, uint8_t* outb, const float* lut_s, int T, int swap_rb, uchar4 fill) {
-    o.outf = outf; o.outb = outb; o.lut = lut_s; o.T = T; o.swap_rb = swap_rb;
-    o.fillc[0] = fill.x; o.fillc[1] = fill.y; o.fillc[2] = fill.z;
-    if (!OUT_U8)
-        for (int p = 0; p < 3; ++p) o.padf[p] = lut_s[p * LUT_STRIDE + o.fillc[swap_rb ? 2 - p : p]];
-}
-
-
-// ------------------------------------------------------------------------------------------------------
 // warp kernel: (ROI, 32-column strip) items, one warp each
 // ------------------------------------------------------------------------------------------------------
-// ---- packed float32x2 arithmetic (sm_100a FFMA2 / FADD2), every lane IEEE round-to-nearest ----
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pack2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void unpack2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ u64 fadd2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-// ptxas 12.9 contracts a mul.rn.f32x2 feeding an add.rn.f32x2 into one FFMA2 (even with --fmad=false and
-// volatile asm; the scalar forms are left alone): one rounding where OpenCV rounds twice, seen as 1-LSB
-// errors in ~1e-4 of the pixels.  fma(a, b, -0.0) with a literal -0 is simplified back to a multiply and
-// contracted again.  The vertical pass therefore forms its rounded products as fma(a, b, z) with
-// z = (-0.0f, -0.0f) held in a register whose value the compiler cannot prove: the same value as a * b for
-// non-negative operands, and an FFMA2 cannot be merged with the add that follows.
-__device__ __forceinline__ u64 fprod2(u64 a, u64 b, u64 negzero2) { return ffma2(a, b, negzero2); }
-
-// float(2^23 + byte K of v): the byte dropped into the mantissa of 8388608.0f (one PRMT, no I2F)
-template <int K>
-__device__ __forceinline__ float magic_byte(unsigned v) { return __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7540 + K)); }
-
-// Column weights of the 3-slot horizontal pass.  fl(b * w) is computed as fma(2^23 + b, w, -(2^23 * w)):
-// the product 2^23 * w is exact, so the fused result is the correctly rounded b * w, bit-identical to
-// OpenCV's separately rounded multiply.
-struct ColW {
-    float w[3], c[3];       // weight and -(2^23 * weight) per slot
-    __device__ __forceinline__ void set(float a, float b, float d) {
-        w[0] = a; w[1] = b; w[2] = d;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            c[k] = __fmul_rn(w[k], -8388608.0f);
-            asm volatile("" : "+f"(c[k]));      // opaque: keep it in a register instead of re-multiplying in the inner loop
-        }
-    }
-};
-
-// shared-memory accesses through 32-bit shared-window addresses (no generic-address arithmetic in the hot loop)
-__device__ __forceinline__ unsigned lds_u32(unsigned addr) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ unsigned lds_u8(unsigned addr) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ float lds_f32(unsigned addr) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v; }
-__device__ __forceinline__ float4 lds_f4(unsigned addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-
-// output store of the fast paths: the crop buffer is written once and never re-read by this kernel
-#if defined(BPC_WHATIF)
-__device__ float* g_whatif_base;
-#endif
-template <int K = 0>
-__device__ __forceinline__ void stg_out(float* p, float v) {
-#if defined(BPC_WHATIF) && BPC_WHATIF == 1          // only plane 0 is stored
-    if (K == 0) *p = v; else asm volatile("" :: "f"(v));
-#elif defined(BPC_WHATIF) && BPC_WHATIF == 2        // LSU traffic without L2 traffic: the value goes to shared memory
-    asm volatile("st.shared.f32 [%0], %1;" :: "r"(((unsigned)(size_t)p) & 0x7cu), "f"(v));
-#elif defined(BPC_WHATIF) && BPC_WHATIF == 4        // stores fold into a 128 KB window per CTA (57 MB in all: stays in L2)
-    float* q = (float*)((size_t)g_whatif_base + ((size_t)blockIdx.x << 17) + (((size_t)p) & 0x1fffc));
-    *q = v;
-#elif defined(BPC_WHATIF) && BPC_WHATIF == 3        // no store, LUT value still loaded
-    asm volatile("" :: "f"(v));
-#elif defined(BPC_STG_CS)
-    __stcs(p, v);
-#else
-    *p = v;
-#endif
-}
-
-// horizontal pass of one source row for one output column: 9 bytes starting at shared address a4 + sh/8
-__device__ __forceinline__ void h_area3(unsigned a4, int sh, const ColW& cw, u64& h01, float& h2) {
-    const unsigned q0 = lds_u32(a4), q1 = lds_u32(a4 + 4), q2 = lds_u32(a4 + 8);
-    const unsigned v0 = __funnelshift_r(q0, q1, sh), v1 = __funnelshift_r(q1, q2, sh), v2 = q2 >> sh;
-    // pixel k = bytes 3k .. 3k+2; the (w, w) / (c, c) pairs become scalar-broadcast operands of FFMA2
-    const u64 p0 = ffma2(pack2(magic_byte<0>(v0), magic_byte<1>(v0)), pack2(cw.w[0], cw.w[0]), pack2(cw.c[0], cw.c[0]));
-    const u64 p1 = ffma2(pack2(magic_byte<3>(v0), magic_byte<0>(v1)), pack2(cw.w[1], cw.w[1]), pack2(cw.c[1], cw.c[1]));
-    const u64 p2 = ffma2(pack2(magic_byte<2>(v1), magic_byte<3>(v1)), pack2(cw.w[2], cw.w[2]), pack2(cw.c[2], cw.c[2]));
-    const float r0 = __fmaf_rn(magic_byte<2>(v0), cw.w[0], cw.c[0]);
-    const float r1 = __fmaf_rn(magic_byte<1>(v1), cw.w[1], cw.c[1]);
-    const float r2 = __fmaf_rn(magic_byte<0>(v2), cw.w[2], cw.c[2]);
-    h01 = fadd2(fadd2(p0, p1), p2);
-    h2 = __fadd_rn(__fadd_rn(r0, r1), r2);
-}
-
-// horizontal pass with NT taps evaluated (4..6): 3*NT bytes starting at shared address a4 + sh/8.  Taps beyond a
-// lane's own count carry weight +0.0f (c = -0.0f): fma(2^23 + b, +0, -0) = +0 and s + (+0) = s, so padding the
-// tap list to the warp's maximum leaves every sum bit-identical to the sequential ((S0*w0 + S1*w1) + ...) order.
-template <int NT>
-__device__ __forceinline__ void h_area_n(unsigned a4, int sh, const float (&w)[6], const float (&c)[6], u64& h01, float& h2) {
-    constexpr int NV = (3 * NT + 3) / 4;            // aligned words holding 3*NT bytes; NV + 1 raw words cover any shift
-    unsigned q[NV + 1], v[NV];
-#pragma unroll
-    for (int i = 0; i <= NV; ++i) q[i] = lds_u32(a4 + 4 * i);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) v[i] = __funnelshift_r(q[i], q[i + 1], sh);
-#pragma unroll
-    for (int k = 0; k < NT; ++k) {
-        const int j = 3 * k;
-        const float b0 = __uint_as_float(__byte_perm(v[j >> 2], 0x4B000000u, 0x7540 + (j & 3)));
-        const float b1 = __uint_as_float(__byte_perm(v[(j + 1) >> 2], 0x4B000000u, 0x7540 + ((j + 1) & 3)));
-        const float b2 = __uint_as_float(__byte_perm(v[(j + 2) >> 2], 0x4B000000u, 0x7540 + ((j + 2) & 3)));
-        const u64 p = ffma2(pack2(b0, b1), pack2(w[k], w[k]), pack2(c[k], c[k]));
-        const float r = __fmaf_rn(b2, w[k], c[k]);
-        h01 = (k == 0) ? p : fadd2(h01, p);
-        h2 = (k == 0) ? r : __fadd_rn(h2, r);
-    }
-}
-
-// horizontal pass of the fixed-point bilinear: 6 bytes at shared address a4 + sh/8, result pre-shifted by 4
-__device__ __forceinline__ void h_lin(unsigned a4, int sh, int w0, int w1, int* h) {
-    const unsigned q0 = lds_u32(a4), q1 = lds_u32(a4 + 4), q2 = lds_u32(a4 + 8);
-    const unsigned v0 = __funnelshift_r(q0, q1, sh), v1 = __funnelshift_r(q1, q2, sh);
-    h[0] = (int)((v0 & 0xffu) * w0 + (v0 >> 24) * w1) >> 4;
-    h[1] = (int)(((v0 >> 8) & 0xffu) * w0 + (v1 & 0xffu) * w1) >> 4;
-    h[2] = (int)(((v0 >> 16) & 0xffu) * w0 + ((v1 >> 8) & 0xffu) * w1) >> 4;
-}
-
-// cvRound(v) for 0 <= v < 2^22 without F2I: adding 2^23 leaves round-half-even(v) in the low mantissa bits
-// (no clamp: the tap weights of each axis sum to 1 within a few ulp, so v <= 255.001 and the result is <= 255)
-__device__ __forceinline__ int round_u8(float v) { return __float_as_int(__fadd_rn(v, 8388608.0f)) & 0xff; }
-// shared address of LUT[cvRound(v)]: lut_m = lut_base - 4 * 0x4B000000 (mod 2^32)
-__device__ __forceinline__ unsigned lut_addr(float v, unsigned lut_m) { return (unsigned)__float_as_int(__fadd_rn(v, 8388608.0f)) * 4u + lut_m; }
-
-// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier in shared memory ----
-__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(unsigned dst, unsigned long long src, unsigned bytes, unsigned bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-#ifndef BPC_MBAR_HINT_NS
-#define BPC_MBAR_HINT_NS 2000
-#endif
-// try_wait with a suspend-time hint: a waiting warp sleeps in hardware until the phase completes (or the hint elapses) instead of
-// spinning through try_wait / yield / branch -- spinning consumer and producer warps executed 30 % of the CTA kernel's
-// instructions before the hint was added
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
-    asm volatile("{\n"
-                 ".reg .pred p;\n"
-                 "BPC_WAIT:\n"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-                 "@p bra BPC_DONE;\n"
-                 "bra BPC_WAIT;\n"
-                 "BPC_DONE:\n"
-                 "}" :: "r"(bar), "r"(parity), "r"((unsigned)BPC_MBAR_HINT_NS) : "memory");
-}
-
 // Stage rows [s_lo, s_lo + count) of a strip into a warp buffer.  Normal case: one TMA bulk copy of `pitch` bytes
 // per row (lane r issues row r), completion counted in bytes on the warp's mbarrier -> returns 1.  If the
 // 16-byte-aligned over-read of the last row would leave the image pool (last rows of the last image) the
@@ -627,12 +249,6 @@ __device__ __forceinline__ void warp_stage_2d(unsigned buf_s, unsigned bar_s, co
     if (lane < nboxes)
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                      :: "r"(buf_s + (unsigned)(lane * rb * pitch)), "l"(map), "r"(xw), "r"(row + lane * rb), "r"(bar_s) : "memory");
-}
-
-__device__ __forceinline__ int warp_max_i32(int v) {
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, m));
-    return v;
 }
 
 // TT = compile-time target size (0: run-time T); ALIGNED = the image row pitch W*3 is a multiple of 16 bytes
@@ -1091,431 +707,6 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
 }
 
 // ------------------------------------------------------------------------------------------------------
-// CTA kernel: classes 1, 3 and 4, one crop per CTA, warp-specialised
-// ------------------------------------------------------------------------------------------------------
-// Warps 0 .. NS-1 (NS = T / 32 strips) are consumers: one lane per output column, source rows in order.  The LAST warp is a
-// producer whose lane 0 walks the list of class-1 / class-3 crops (atomic counter) and, per crop, copies the crop's block of
-// row descriptors into shared memory (one bulk copy) and then, per ring slot, issues ONE 2-D tensor copy of eight FULL-WIDTH
-// source rows -- seven times fewer TMA operations than one box per strip, every source byte fetched once per crop, and the
-// ~300-cycle scoreboard wait behind each TMA issue (measured: 13 % of the per-strip kernel's warp time) sits in a warp that has
-// nothing else to do.  The producer runs ahead across crops (ring of four slots, two descriptor blocks), which also hides
-// the per-crop set-up round trips.  Consumers meet on the slots' full / empty mbarriers, so the strips of one crop stay within
-// four slots of each other: whole 896-byte output rows of a plane reach L2 close together, and the rows above / below the
-// resized image are written as contiguous runs by all consumer threads.
-//   class 1 (area, <= 3 taps): per SOURCE row a (ba, bb) record (see bpc_crop_prep_kernel); a row whose ba has the sign bit
-//            set closes the open output row (LUT, three 128-byte stores) and opens the next with weight bb;
-//   class 3 (fixed-point bilinear, the box grows): per OUTPUT row (b0, b1, second source row, first source row); an output row
-//            is emitted as soon as the slot holding its second source row has landed -- its first row is the previous output
-//            row's first or second row, whose horizontal pass is still in registers.
-constexpr int CTA_ROWS = 8;                  // source rows per ring slot (= one TMA box)
-// ring slots and resident CTAs per SM: the T = 224 float instantiation (the benchmark's) runs 4 CTAs/SM (8 warps, 63 registers,
-// three slots: 55 KB of shared memory), which buys classes 3 and 4 latency hiding (0.66 -> 0.70, 0.67 -> 0.69) and leaves class 1
-// where it was; the run-time-T and T = 256 instantiations (up to 9 warps) keep four slots and 3 CTAs/SM
-__host__ __device__ constexpr int cta_nslot(int TT) { return TT == 224 ? 3 : 4; }
-constexpr int CTA_NMAPS = 25;                // box widths 64, 128, ... 1600 bytes (8-byte elements)
-constexpr int CTA_MAX_T = 256;               // 8 consumer warps
-struct CtaMaps { CUtensorMap m[CTA_NMAPS]; };
-__host__ __device__ __forceinline__ int cta_pitch_max(int T) { return ((15 + 3 * (2 * T - 1) + 12 + 63) >> 6) << 6; }
-// staged bytes per source row of a crop: misalignment of its first byte + 3 w + what the widest horizontal pass over-reads
-// (class 1: three words from the aligned tap address; class 4: up to six taps padded to the warp maximum)
-__host__ __device__ __forceinline__ int cta_pitch(int mis0, int w, int cls) { return ((mis0 + 3 * w + (cls == 4 ? 40 : 12) + 63) >> 6) << 6; }
-__host__ __device__ __forceinline__ int cta_desc_bytes(int T) { return ydesc_stride(T) * 16; }
-__host__ __device__ __forceinline__ int cta_smem_bytes(int T, int nslot) { return LUT_SMEM + nslot * CTA_ROWS * cta_pitch_max(T) + 2 * cta_desc_bytes(T) + 256; }
-
-// Lockstep of a crop's strips (a named barrier over the consumer warps): the seven 128-byte pieces of an output row then reach
-// L2 within a short window and are written back together -- DRAM sees whole rows instead of scattered lines (measured on
-// stores alone: 5.7 -> 7.2 TB/s; on the 60-400 px mix 0.79 -> 0.83 of roofline).  Class 1 only, once per ring slot: a barrier every
-// eight output rows made class 3 slower (0.64 -> 0.57: many idle strips, latency-bound) and class 4 is issue-bound.
-#define CTA_LOCKSTEP() do { if (cls == 1) asm volatile("bar.sync 1, %0;" :: "r"(NS * 32) : "memory"); } while (0)
-__device__ __forceinline__ void mbar_arrive(unsigned bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
-
-template <bool OUT_U8, int TT, bool SWAP, bool BF16 = false>
-__global__ void __launch_bounds__(TT == 224 ? 256 : 288, TT == 224 ? 4 : 3)
-bpc_crop_cta_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const RoiGeom* __restrict__ geom,
-                    const float4* __restrict__ xdesc, const float4* __restrict__ ydesc, const int32_t* __restrict__ list1,
-                    int32_t* __restrict__ counters, int Trt, uchar4 fill, int swap_rb, const float* __restrict__ lut_g,
-                    float* __restrict__ outf, uint8_t* __restrict__ outb, const __grid_constant__ CtaMaps tm) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int CTA_NSLOT = cta_nslot(TT);
-    float* lut = reinterpret_cast<float*>(smem);
-    const int T = TT ? TT : Trt;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int NS = (T + 31) >> 5;                                   // consumer warps; warp NS is the producer
-    const int pitch_max = cta_pitch_max(T);
-    const int slot_bytes = CTA_ROWS * pitch_max;
-    const int desc_bytes = cta_desc_bytes(T);
-    const unsigned smem_s = (unsigned)__cvta_generic_to_shared(smem);
-    const unsigned ring_s = smem_s + LUT_SMEM;
-    const unsigned desc_s = ring_s + CTA_NSLOT * slot_bytes;       // [2][ystride] float4: the current and the next crop's row descriptors
-    const unsigned misc_s = desc_s + 2 * desc_bytes;
-    const unsigned full_s = misc_s, empty_s = misc_s + 8 * CTA_NSLOT, hfull_s = misc_s + 16 * CTA_NSLOT, hempty_s = hfull_s + 16;
-    volatile int* hdr = reinterpret_cast<volatile int*>(smem + (misc_s - smem_s) + 16 * CTA_NSLOT + 32);       // [2] crop index
-    if (tid == 0) {
-        for (int i = 0; i < CTA_NSLOT; ++i) { mbar_init(full_s + 8 * i, 1); mbar_init(empty_s + 8 * i, NS); }
-        for (int i = 0; i < 2; ++i) { mbar_init(hfull_s + 8 * i, 1); mbar_init(hempty_s + 8 * i, NS); }
-        *reinterpret_cast<volatile unsigned*>(smem + 3 * LUT_STRIDE * 4) = smem_s - 4u * 0x4B000000u;              // see lut_addr()
-    }
-    if (!OUT_U8)
-        for (int e = tid; e < 768; e += (int)blockDim.x) lut[(e >> 8) * LUT_STRIDE + (e & 255)] = lut_g[e];
-    __syncthreads();
-    Out<OUT_U8, BF16> out;
-    out_init(out, outf, outb, lut, T, swap_rb, fill);
-    if (!OUT_U8 && tid < 3) lut[tid * LUT_STRIDE + 256] = out.padf[tid];
-    __syncthreads();
-    const unsigned lut_m = *reinterpret_cast<volatile unsigned*>(smem + 3 * LUT_STRIDE * 4);
-    const int ds = desc_stride(T), ystride = ydesc_stride(T);
-    const unsigned long long rowstride = (unsigned long long)W * 3ull;
-    const unsigned long long img_end = (unsigned long long)(uintptr_t)images + (unsigned long long)B * H * rowstride;
-    const int n1 = counters[8];
-    int32_t* work = counters + 12;
-
-    if (wid == NS) {
-        // ------------------------------------ producer ------------------------------------
-        if (lane != 0) return;
-        int idx = atomicAdd(work, 1);
-        unsigned cg = 0;                                            // slots filled so far
-        for (int hi = 0;; ++hi) {
-            const int hb = hi & 1;
-            if (hi >= 2) mbar_wait(hempty_s + 8 * hb, ((hi >> 1) - 1) & 1);
-            if (idx >= n1) {
-                hdr[hb] = -1;
-                mbar_arrive(hfull_s + 8 * hb);
-                break;
-            }
-            const int idx_next = atomicAdd(work, 1);                // round trip hidden behind this crop's copies
-            const int roi = list1[idx];
-            const RoiGeom* gp = geom + roi;
-            const unsigned long long src = gp->src;
-            const int w = gp->w, h = gp->cls == 0 ? 0 : gp->h;     // a rejected box (class 0) has no source rows: header only
-            hdr[hb] = roi;
-            // the part of the crop's row-descriptor block that will be read: per output row (class 3) or per source row, padded slot included
-            const unsigned dbytes = gp->cls == 0 ? 0u : (unsigned)min(desc_bytes, gp->cls == 3 ? 16 * (gp->new_h + 1) : 8 * (((h + CTA_ROWS - 1) & ~(CTA_ROWS - 1)) + CTA_ROWS));
-            mbar_expect_tx(hfull_s + 8 * hb, dbytes);
-            if (dbytes) bulk_g2s(desc_s + hb * desc_bytes, (unsigned long long)(uintptr_t)(ydesc + (size_t)roi * ystride), dbytes, hfull_s + 8 * hb);
-            const int mis0 = (int)(src & 15ull);
-            const int pitch = cta_pitch(mis0, w, gp->cls);
-            const unsigned long long off = (src & ~15ull) - (unsigned long long)(uintptr_t)images;
-            const int row0 = (int)(off / rowstride);
-            const int x8 = (int)((off - (unsigned long long)row0 * rowstride) >> 3);
-            if (gp->cls == 0) {
-                // nothing to stage
-            } else if (pitch <= pitch_max) {
-                // one 2-D tensor copy of eight full-width rows per slot (rows / columns beyond the pool are zero-filled)
-                const CUtensorMap* map = &tm.m[(pitch >> 6) - 1];
-                const int nchunks = (h + CTA_ROWS - 1) / CTA_ROWS;
-                for (int c = 0; c < nchunks; ++c, ++cg) {
-                    const unsigned j = cg % CTA_NSLOT;
-                    if (cg >= CTA_NSLOT) mbar_wait(empty_s + 8 * j, ((cg / CTA_NSLOT) - 1) & 1);
-                    mbar_expect_tx(full_s + 8 * j, (unsigned)(CTA_ROWS * pitch));
-                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                                 :: "r"(ring_s + j * slot_bytes), "l"(map), "r"(x8), "r"(row0 + c * CTA_ROWS), "r"(full_s + 8 * j) : "memory");
-                }
-            } else {
-                // wide class-4 crops (rows of up to 5 T pixels): rps rows per slot, one 1-D bulk copy each, clipped to the pool
-                const int rps = slot_bytes / pitch;
-                const int nchunks = (h + rps - 1) / rps;
-                const unsigned long long a0 = src & ~15ull;
-                for (int c = 0; c < nchunks; ++c, ++cg) {
-                    const unsigned j = cg % CTA_NSLOT;
-                    if (cg >= CTA_NSLOT) mbar_wait(empty_s + 8 * j, ((cg / CTA_NSLOT) - 1) & 1);
-                    unsigned total = 0;
-                    for (int r = 0; r < rps; ++r) {
-                        const unsigned long long a = a0 + (unsigned long long)(c * rps + r) * rowstride;
-                        if (a < img_end) total += (unsigned)min((unsigned long long)pitch, (img_end - a) & ~15ull);
-                    }
-                    mbar_expect_tx(full_s + 8 * j, total);
-                    for (int r = 0; r < rps; ++r) {
-                        const unsigned long long a = a0 + (unsigned long long)(c * rps + r) * rowstride;
-                        if (a < img_end) {
-                            const unsigned nb = (unsigned)min((unsigned long long)pitch, (img_end - a) & ~15ull);
-                            if (nb) bulk_g2s(ring_s + j * slot_bytes + (unsigned)(r * pitch), a, nb, full_s + 8 * j);
-                        }
-                    }
-                }
-            }
-            idx = idx_next;
-        }
-        return;
-    }
-
-    // ------------------------------------ consumers: warp = strip ------------------------------------
-    constexpr bool swap = SWAP;
-    const size_t plane = (size_t)T * T;
-    const float nz = __int_as_float((int)(0x80000000u | (unsigned)fill.w));     // -0.0f: fill.w is 0 at run time
-    const u64 nz2 = pack2(nz, nz);
-    const int nthc = NS * 32;
-    const int x = wid * 32 + lane;
-    unsigned cg = 0;
-    for (int hi = 0;; ++hi) {
-        const int hb = hi & 1;
-        mbar_wait(hfull_s + 8 * hb, (hi >> 1) & 1);
-        const int roi = hdr[hb];
-        if (roi < 0) break;
-        const RoiGeom* gp = geom + roi;
-        const int cls = gp->cls;
-        const int new_w = gp->new_w, new_h = gp->new_h, dx0 = gp->dx, dy0 = gp->dy, h = gp->h;
-        const int mis0 = (int)(gp->src & 15ull);
-        const int pitch = cta_pitch(mis0, gp->w, cls);
-        const int rps = pitch <= pitch_max ? CTA_ROWS : slot_bytes / pitch;       // source rows per ring slot
-        const int nchunks = (h + rps - 1) / rps;
-        const unsigned dsc = desc_s + hb * desc_bytes;
-        if (cls == 0) {                                             // rejected box: the whole canvas is fill (no slots were issued)
-            out.pad_rows(roi, 0, T, tid, nthc);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(hempty_s + 8 * hb);
-            continue;
-        }
-        out.pad_rows(roi, 0, dy0, tid, nthc);                       // whole rows above / below: contiguous runs
-        out.pad_rows(roi, dy0 + new_h, T, tid, nthc);
-        const int xr = x - dx0;
-        const bool active = xr >= 0 && xr < new_w;
-        const bool touches = wid * 32 < dx0 + new_w && wid * 32 + 32 > dx0;
-        const bool store_ok = (TT && TT % 32 == 0) || x < T;
-        float* optr = outf + ((size_t)roi * 3 * T + dy0) * T + x;     // (plane 0, first image row, column x)
-        unsigned short* optr16 = reinterpret_cast<unsigned short*>(outf) + (((size_t)roi * T + dy0) * T + x) * 3;   // BF16: pixel (row, x), channels-last
-        const unsigned short padh0 = bf16_bits(out.padf[0]), padh1 = bf16_bits(out.padf[1]), padh2 = bf16_bits(out.padf[2]);
-        if (!touches) {
-            // a strip beside the resized image: the fill value, at the pace of the neighbours
-            int ydone = 0;
-            for (int c = 0; c < nchunks; ++c, ++cg) {
-                const unsigned j = cg % CTA_NSLOT;
-                CTA_LOCKSTEP(); mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty_s + 8 * j);
-                int ndone;
-                if (cls != 3) {
-                    const float ba = (lane < rps) ? lds_f32(dsc + 8u * (unsigned)(c * rps + lane)) : 0.f;
-                    ndone = __popc(__ballot_sync(0xffffffffu, __float_as_int(ba) < 0));
-                } else {
-                    // output rows whose second source row lies in this slot (monotone in y)
-                    const int last_row = c * CTA_ROWS + CTA_ROWS - 1;
-                    ndone = 0;
-                    for (int y0 = ydone; y0 < new_h; y0 += 32) {
-                        const int yy = y0 + lane;
-                        const bool ok = yy < new_h && __float_as_int(lds_f4(dsc + 16u * (unsigned)min(yy, new_h - 1)).z) <= last_row;
-                        const int n = __popc(__ballot_sync(0xffffffffu, ok));
-                        ndone += n;
-                        if (n < 32) break;
-                    }
-                }
-                for (int r = 0; r < ndone; ++r) {
-                    if (store_ok) {
-                        if (OUT_U8) out.pad(roi, dy0 + ydone + r, x);
-                        else if (BF16) { optr16[0] = padh0; optr16[1] = padh1; optr16[2] = padh2; optr16 += 3 * T; }
-                        else { optr[0] = out.padf[0]; optr[plane] = out.padf[1]; optr[2 * plane] = out.padf[2]; optr += T; }
-                    }
-                }
-                ydone += ndone;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(hempty_s + 8 * hb);         // done with this crop's descriptor block
-            continue;
-        }
-        const float4 xd = xdesc[(size_t)roi * ds + min(max(xr, 0), new_w - 1)];
-        const int xs = __float_as_int(xd.w) & 0xffffff;
-        const int colc = 3 * xs + mis0;
-        const unsigned colc4 = (unsigned)(colc & ~3);
-        const int shc = (colc & 3) * 8;
-        if (cls == 1) {
-            ColW cw;
-            cw.set(xd.x, xd.y, xd.z);
-            if (!active) {                               // beside the image: every row sums to 256 -> LUT entry 256 = fill
-                cw.w[0] = cw.w[1] = cw.w[2] = 0.f;
-                cw.c[0] = 256.f; cw.c[1] = cw.c[2] = 0.f;
-            }
-            u64 acc01 = 0ull;
-            float acc2 = 0.f;
-            unsigned roff = 0;                                // element offset of the open output row from optr
-            int yout = 0;
-            for (int c = 0; c < nchunks; ++c, ++cg) {
-                const unsigned j = cg % CTA_NSLOT;
-                CTA_LOCKSTEP(); mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
-                const unsigned rbase = ring_s + j * slot_bytes + colc4;
-                const unsigned rec = dsc + 8u * CTA_ROWS * (unsigned)c;
-#pragma unroll
-                for (int half = 0; half < CTA_ROWS / 4; ++half) {
-                    const float4 dA = lds_f4(rec + 32u * half), dB = lds_f4(rec + 32u * half + 16);
-                    u64 h01[4];
-                    float h2[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) h_area3(rbase + (unsigned)((4 * half + k) * pitch), shc, cw, h01[k], h2[k]);
-                    if (half == CTA_ROWS / 4 - 1) {
-                        __syncwarp();                           // every lane has read slot j
-                        if (lane == 0) mbar_arrive(empty_s + 8 * j);
-                    }
-                    const float ba[4] = {dA.x, dA.z, dB.x, dB.z}, bb[4] = {dA.y, dA.w, dB.y, dB.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const float wa = fabsf(ba[k]);
-                        acc01 = fadd2(acc01, fprod2(pack2(wa, wa), h01[k], nz2));
-                        acc2 = __fadd_rn(acc2, __fmul_rn(wa, h2[k]));
-                        if (__float_as_int(ba[k]) < 0) {            // output row complete
-                            float a0f, a1f;
-                            unpack2(acc01, a0f, a1f);
-                            if (OUT_U8) {
-                                if (active) out.px(roi, dy0 + yout, x, round_u8(a0f), round_u8(a1f), round_u8(acc2));
-                                else if (x < T) out.pad(roi, dy0 + yout, x);
-                                ++yout;
-                            } else {
-                                const unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
-                                if (store_ok) {
-                                    const float v0 = lds_f32(swap ? l2 : l0), v1 = lds_f32(l1 + 4 * LUT_STRIDE), v2 = lds_f32((swap ? l0 : l2) + 8 * LUT_STRIDE);
-                                    if (BF16) {
-                                        unsigned short* o = optr16 + roff;
-                                        o[0] = bf16_bits(v0); o[1] = bf16_bits(v1); o[2] = bf16_bits(v2);
-                                    } else {
-                                        float* o = optr + roff;
-                                        stg_out<0>(o, v0); stg_out<1>(o + plane, v1); stg_out<2>(o + 2 * plane, v2);
-                                    }
-                                }
-                                roff += BF16 ? 3u * (unsigned)T : (unsigned)T;
-                            }
-                            acc01 = fprod2(pack2(bb[k], bb[k]), h01[k], nz2);
-                            acc2 = __fmul_rn(bb[k], h2[k]);
-                        }
-                    }
-                }
-            }
-        } else if (cls == 4) {
-            // ---------------- class 4: area, 4 .. 6 taps per axis, source rows in order ----------------
-            const int xn = __float_as_int(xd.w) >> 24;
-            const int nt = warp_max_i32(xn);                      // uniform: taps evaluated per source row
-            float w[6], cc[6];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                w[k] = (k == 0) ? xd.x : ((k < xn - 1) ? xd.y : ((k == xn - 1) ? xd.z : 0.f));
-                if (!active) w[k] = 0.f;
-                cc[k] = __fmul_rn(w[k], -8388608.0f);
-                if (!active && k == 0) cc[k] = 256.f;             // beside the image: every row sums to 256 -> LUT entry 256 = fill
-                asm volatile("" : "+f"(cc[k]));
-            }
-            u64 acc01 = 0ull;
-            float acc2 = 0.f;
-            unsigned roff = 0;
-            int yout = 0;
-            auto vstep = [&](float ba, float bb, u64 h01, float h2) {
-                const float wa = fabsf(ba);
-                acc01 = fadd2(acc01, fprod2(pack2(wa, wa), h01, nz2));
-                acc2 = __fadd_rn(acc2, __fmul_rn(wa, h2));
-                if (__float_as_int(ba) < 0) {                       // output row complete
-                    float a0f, a1f;
-                    unpack2(acc01, a0f, a1f);
-                    if (OUT_U8) {
-                        if (active) out.px(roi, dy0 + yout, x, round_u8(a0f), round_u8(a1f), round_u8(acc2));
-                        else if (x < T) out.pad(roi, dy0 + yout, x);
-                        ++yout;
-                    } else {
-                        const unsigned l0 = lut_addr(a0f, lut_m), l1 = lut_addr(a1f, lut_m), l2 = lut_addr(acc2, lut_m);
-                        if (store_ok) {
-                            const float v0 = lds_f32(swap ? l2 : l0), v1 = lds_f32(l1 + 4 * LUT_STRIDE), v2 = lds_f32((swap ? l0 : l2) + 8 * LUT_STRIDE);
-                            if (BF16) {
-                                unsigned short* o = optr16 + roff;
-                                o[0] = bf16_bits(v0); o[1] = bf16_bits(v1); o[2] = bf16_bits(v2);
-                            } else {
-                                float* o = optr + roff;
-                                stg_out<0>(o, v0); stg_out<1>(o + plane, v1); stg_out<2>(o + 2 * plane, v2);
-                            }
-                        }
-                        roff += BF16 ? 3u * (unsigned)T : (unsigned)T;
-                    }
-                    acc01 = fprod2(pack2(bb, bb), h01, nz2);
-                    acc2 = __fmul_rn(bb, h2);
-                }
-            };
-            auto strip = [&](auto nt_c) {
-                constexpr int NT = decltype(nt_c)::value;
-                for (int c = 0; c < nchunks; ++c, ++cg) {
-                    const unsigned j = cg % CTA_NSLOT;
-                    CTA_LOCKSTEP(); mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
-                    const unsigned rbase = ring_s + j * slot_bytes + colc4;
-                    const unsigned rec = dsc + 8u * (unsigned)(c * rps);
-                    int r = 0;
-                    for (; r + 1 < rps; r += 2) {                   // two rows at a time: their loads and conversions interleave
-                        const float4 d = make_float4(lds_f32(rec + 8u * r), lds_f32(rec + 8u * r + 4), lds_f32(rec + 8u * r + 8), lds_f32(rec + 8u * r + 12));
-                        u64 ha01, hb01;
-                        float ha2, hb2;
-                        h_area_n<NT>(rbase + (unsigned)(r * pitch), shc, w, cc, ha01, ha2);
-                        h_area_n<NT>(rbase + (unsigned)((r + 1) * pitch), shc, w, cc, hb01, hb2);
-                        vstep(d.x, d.y, ha01, ha2);
-                        vstep(d.z, d.w, hb01, hb2);
-                    }
-                    if (r < rps) {
-                        const float ba = lds_f32(rec + 8u * r), bb = lds_f32(rec + 8u * r + 4);
-                        u64 ha01;
-                        float ha2;
-                        h_area_n<NT>(rbase + (unsigned)(r * pitch), shc, w, cc, ha01, ha2);
-                        vstep(ba, bb, ha01, ha2);
-                    }
-                    __syncwarp();                               // every lane has read slot j
-                    if (lane == 0) mbar_arrive(empty_s + 8 * j);
-                }
-            };
-            if (nt <= 4) strip(std::integral_constant<int, 4>{});
-            else if (nt == 5) strip(std::integral_constant<int, 5>{});
-            else strip(std::integral_constant<int, 6>{});
-        } else {
-            // ---------------- class 3: fixed-point bilinear ----------------
-            const int xw0 = __float_as_int(xd.x), xw1 = __float_as_int(xd.y);
-            const unsigned lut_s = smem_s;
-            int rowA = -1, rowB = -1;
-            int HA[3] = {0, 0, 0}, HB[3] = {0, 0, 0};
-            int y = 0;
-            float4 d = lds_f4(dsc);
-            for (int c = 0; c < nchunks; ++c, ++cg) {
-                const unsigned j = cg % CTA_NSLOT;
-                CTA_LOCKSTEP(); mbar_wait(full_s + 8 * j, (cg / CTA_NSLOT) & 1);
-                const int last_row = c * CTA_ROWS + CTA_ROWS - 1;
-                const unsigned sbase = ring_s + j * slot_bytes + colc4 - (unsigned)(c * CTA_ROWS * pitch);     // source row r at sbase + r * pitch
-                while (y < new_h) {
-                    // (b * H) >> 16 as the high word of (b << 16) * H: one IMAD.HI instead of a multiply and a shift (0 <= b <= 2048, 0 <= H < 2^15)
-                    const unsigned b0 = (unsigned)__float_as_int(d.x) << 16, b1 = (unsigned)__float_as_int(d.y) << 16;
-                    const int sy0 = __float_as_int(d.w), sy1 = __float_as_int(d.z);
-                    if (sy1 > last_row) break;
-                    ++y;
-                    d = lds_f4(dsc + 16u * (unsigned)y);              // next row's descriptor behind this row's arithmetic
-                    if (active) {
-                        if (sy0 != rowA) {
-                            if (sy0 == rowB) { HA[0] = HB[0]; HA[1] = HB[1]; HA[2] = HB[2]; }
-                            else h_lin(sbase + (unsigned)(sy0 * pitch), shc, xw0, xw1, HA);
-                            rowA = sy0;
-                        }
-                        if (sy1 != rowB) {
-                            if (sy1 == rowA) { HB[0] = HA[0]; HB[1] = HA[1]; HB[2] = HA[2]; }
-                            else h_lin(sbase + (unsigned)(sy1 * pitch), shc, xw0, xw1, HB);
-                            rowB = sy1;
-                        }
-                        unsigned o[3];                      // 4 * value + 2 low bits
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) o[k] = __umulhi(b1, (unsigned)HB[k]) + (__umulhi(b0, (unsigned)HA[k]) + 2u);
-                        if (OUT_U8) {
-                            out.px(roi, dy0 + y - 1, x, (int)(o[0] >> 2) & 255, (int)(o[1] >> 2) & 255, (int)(o[2] >> 2) & 255);
-                        } else {
-                            const float v0 = lds_f32(lut_s + ((swap ? o[2] : o[0]) & 0x3fcu)), v1 = lds_f32(lut_s + 4 * LUT_STRIDE + (o[1] & 0x3fcu)),
-                                        v2 = lds_f32(lut_s + 8 * LUT_STRIDE + ((swap ? o[0] : o[2]) & 0x3fcu));
-                            if (BF16) {
-                                optr16[0] = bf16_bits(v0); optr16[1] = bf16_bits(v1); optr16[2] = bf16_bits(v2);
-                                optr16 += 3 * T;
-                            } else {
-                                stg_out<0>(optr, v0); stg_out<1>(optr + plane, v1); stg_out<2>(optr + 2 * plane, v2);
-                                optr += T;
-                            }
-                        }
-                    } else if (x < T) {
-                        if (OUT_U8) out.pad(roi, dy0 + y - 1, x);
-                        else if (BF16) { optr16[0] = padh0; optr16[1] = padh1; optr16[2] = padh2; optr16 += 3 * T; }
-                        else { optr[0] = out.padf[0]; optr[plane] = out.padf[1]; optr[2 * plane] = out.padf[2]; optr += T; }
-                    }
-                }
-                __syncwarp();                               // every lane is done with slot j
-                if (lane == 0) mbar_arrive(empty_s + 8 * j);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(hempty_s + 8 * hb);             // done with this crop's descriptor block
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
 // generic kernel: any regime / scale, persistent CTAs over (ROI, band) items of the generic list
 // ------------------------------------------------------------------------------------------------------
 template <bool OUT_U8, bool BF16>
@@ -1777,43 +968,6 @@ static int tensor_maps(const uint8_t* images, int B, int H, int W, bool aligned,
     return BPC_OK;
 }
 
-// Tensor maps of the CTA kernel: the pool as [B*H rows][W*3/8 uint64], box = {64 i bytes, CTA_ROWS rows}, i = 1 .. CTA_NMAPS.
-static int cta_tensor_maps(const uint8_t* images, int B, int H, int W, CtaMaps* out) {
-    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-    static std::mutex mu;
-    static CtaMaps cached;
-    static const uint8_t* k_images = nullptr;
-    static int k_B = 0, k_H = 0, k_W = 0, k_dev = -1;
-    static EncodeFn encode = nullptr;
-    std::lock_guard<std::mutex> lock(mu);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (images == k_images && B == k_B && H == k_H && W == k_W && dev == k_dev) { *out = cached; return BPC_OK; }
-    if (!encode) {
-        cudaDriverEntryPointQueryResult q;
-        void* fnp = nullptr;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fnp, cudaEnableDefault, &q);
-        if (e != cudaSuccess) return (int)e;
-        if (q != cudaDriverEntryPointSuccess || !fnp) return (int)cudaErrorNotSupported;
-        encode = (EncodeFn)fnp;
-    }
-    const cuuint64_t gdim[2] = {(cuuint64_t)W * 3 / 8, (cuuint64_t)B * H};
-    const cuuint64_t gstride[1] = {(cuuint64_t)W * 3};
-    const cuuint32_t estr[2] = {1, 1};
-    for (int i = 0; i < CTA_NMAPS; ++i) {
-        const cuuint32_t box[2] = {(cuuint32_t)(8 * (i + 1)), (cuuint32_t)CTA_ROWS};
-        const CUresult r = encode(&cached.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, (void*)images, gdim, gstride, box, estr,
-                                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, BPC_L2_PROMO,
-                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { k_images = nullptr; return (int)cudaErrorInvalidValue; }
-    }
-    k_images = images; k_B = B; k_H = H; k_W = W; k_dev = dev;
-    *out = cached;
-    return BPC_OK;
-}
-
 // workspace: geom[R] | xdesc[R][ds] | ydesc[R][ydesc_stride(T)] | counters[16] | glist[R] | list1[R]    (ds = desc_stride(T), float4 records)
 static size_t ws_off_xdesc(int R) { return (((size_t)R * sizeof(RoiGeom)) + 15) & ~(size_t)15; }
 static size_t ws_off_ydesc(int R, int T) { return ws_off_xdesc(R) + (size_t)R * desc_stride(T) * sizeof(float4); }
@@ -1852,31 +1006,9 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
     BPC_LAUNCH_CHECK();
     const uchar4 f4 = make_uchar4(fill[0], fill[1], fill[2], 0);
     if (use_cta) {
-        typedef void (*CtaFn)(const uint8_t*, int, int, int, const RoiGeom*, const float4*, const float4*, const int32_t*, int32_t*, int,
-                              uchar4, int, const float*, float*, uint8_t*, const CtaMaps);
-        CtaMaps cmaps;
-        const int terr = cta_tensor_maps(images, B, H, W, &cmaps);
-        if (terr != BPC_OK) return terr;
-        const bool sw = swap_rb != 0;
-        CtaFn fn;
-        if (OUT_U8) fn = bpc_crop_cta_kernel<OUT_U8, 0, false>;
-        else if (BF16) fn = sw ? bpc_crop_cta_kernel<OUT_U8, 0, true, BF16> : bpc_crop_cta_kernel<OUT_U8, 0, false, BF16>;
-        else if (T == 224) fn = sw ? bpc_crop_cta_kernel<OUT_U8, 224, true> : bpc_crop_cta_kernel<OUT_U8, 224, false>;
-        else if (T == 256) fn = sw ? bpc_crop_cta_kernel<OUT_U8, 256, true> : bpc_crop_cta_kernel<OUT_U8, 256, false>;
-        else fn = sw ? bpc_crop_cta_kernel<OUT_U8, 0, true> : bpc_crop_cta_kernel<OUT_U8, 0, false>;
-        const int nslot = cta_nslot((!OUT_U8 && !BF16 && T == 224) ? 224 : 0);      // as the instantiation picked above
-        const int smem_bytes = cta_smem_bytes(T, nslot);
-        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, cta_smem_bytes(T == 224 ? 224 : CTA_MAX_T, nslot));
-        if (e != cudaSuccess) return (int)e;
-        const int threads = 32 * ((T + 31) / 32 + 1);
-        int dev = 0, sms = 148, per_sm = 3;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem_bytes) != cudaSuccess || per_sm < 1) per_sm = 1;
-        const long long slots = (long long)sms * per_sm;
-        const int grid = (int)((long long)R < slots ? R : slots);
-        fn<<<grid, threads, smem_bytes, st>>>(images, B, H, W, geom, xdesc, ydesc, list1, gcount, T, f4, swap_rb, lut, outf, outb, cmaps);
-        BPC_LAUNCH_CHECK();
+        const int rc = crop_cta_launch(OUT_U8 ? 1 : (BF16 ? 2 : 0), images, B, H, W, geom, xdesc, ydesc, list1, gcount, R, T, f4, swap_rb, lut,
+                                       outf, outb, st);
+        if (rc != BPC_OK) return rc;
     }
     if (!BF16) {
         typedef void (*WarpFn)(const uint8_t*, int, int, int, const RoiGeom*, const float4*, const float4*, int32_t*, int, int, int,
