@@ -33,7 +33,12 @@
 
 namespace bpc {
 
-// Per-SOURCE-row records of an area resize with at most `maxtaps` taps per output row (collective over the 256 threads of a prep
+#ifndef BPC_PREP_THREADS
+#define BPC_PREP_THREADS 128
+#endif
+constexpr int PREP_THREADS = BPC_PREP_THREADS;      // threads of a prep CTA (one ROI each); 128: twice the CTAs in flight of 256 behind the serial geometry section (-33 us per 16 384 ROIs)
+
+// Per-SOURCE-row records of an area resize with at most `maxtaps` taps per output row (collective over the PREP_THREADS threads of a prep
 // CTA): record s = (ba, bb); |ba| = weight of source row s in the output row being accumulated, sign bit of ba set = that output
 // row is complete after row s; bb = weight of row s as the first tap of the next output row (+0 if it has none there).  Rows
 // [h, hpad) stay zero (no contribution, no completed row) so that whole ring slots run to completion.  *bad is set when the taps
@@ -41,9 +46,9 @@ namespace bpc {
 __device__ void src_row_records(float2* ysrc, int cap, const RoiGeom& g, int maxtaps, int tid, int* bad) {
     const int hpad = min(cap, ((g.h + STREAM_ROWS - 1) / STREAM_ROWS) * STREAM_ROWS + STREAM_ROWS);
     if (g.h + STREAM_ROWS > cap) *bad = 1;
-    for (int s = tid; s < hpad; s += 256) ysrc[s] = make_float2(0.f, 0.f);
+    for (int s = tid; s < hpad; s += PREP_THREADS) ysrc[s] = make_float2(0.f, 0.f);
     __syncthreads();
-    for (int d = tid; d < g.new_h && !*bad; d += 256) {
+    for (int d = tid; d < g.new_h && !*bad; d += PREP_THREADS) {
         int ys, yn, fl; float bf, bm, bl;
         area_taps(d, g.scale_y, g.h, ys, yn, bf, bm, bl, fl);
         const int prev_last = d > 0 ? area_last_tap(d - 1, g.scale_y, g.h) : -1;
@@ -73,7 +78,7 @@ __device__ void src_row_records(float2* ysrc, int cap, const RoiGeom& g, int max
 //                                 sum = b0 h0; sum += b1 h1; ... for non-negative terms.
 //   class 3 (fixed-point)      x: (bits(w0), bits(w1), 0, bits(source column))      w = 2048, 0 beyond xmax
 //                              y: (bits(b0), bits(b1), bits(second source row), bits(first source row))
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(PREP_THREADS)
 bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, const int32_t* __restrict__ rois, int R,
                      const int32_t* __restrict__ n_rois_dev, int roi_first, int T, int stream_ok,
                      RoiGeom* __restrict__ geom, float4* __restrict__ xdesc, float4* __restrict__ ydesc,
@@ -143,7 +148,7 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
         // (w_first, w_middle, w_last, bits(start | taps << 24)); a missing first / last tap takes the middle weight
         for (int axis = 0; axis < ((stream_ok & 2) ? 1 : 2); ++axis) {
             const int nd = axis ? g.new_h : g.new_w;
-            for (int d = tid; d < nd; d += 256) {
+            for (int d = tid; d < nd; d += PREP_THREADS) {
                 int st, n, flags; float af, am, al;
                 area_taps(d, axis ? g.scale_y : g.scale_x, axis ? g.h : g.w, st, n, af, am, al, flags);
                 const float w0 = (flags & 1) ? af : ((n == 1 && (flags & 2)) ? al : am);
@@ -156,13 +161,13 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             if (s_bad && tid == 0) { g.cls = 2; }
         }
     } else if (cls == 1) {
-        for (int d = tid; d < g.new_w; d += 256) {
+        for (int d = tid; d < g.new_w; d += PREP_THREADS) {
             int xs, xn; float w0, w1, w2;
             area_taps3(d, g.scale_x, g.w, xs, xn, w0, w1, w2);
             xd[d] = make_float4(w0, w1, w2, __int_as_float(xs));
         }
         if (!(stream_ok & 1)) {
-            for (int d = tid; d < g.new_h; d += 256) {
+            for (int d = tid; d < g.new_h; d += PREP_THREADS) {
                 int ys, yn; float b0, b1, b2;
                 area_taps3(d, g.scale_y, g.h, ys, yn, b0, b1, b2);
                 yd[d] = make_float4(b0, b1, b2, __int_as_float(ys | (yn << 24)));
@@ -172,13 +177,13 @@ bpc_crop_prep_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
             if (s_bad && tid == 0) { g.cls = 2; }
         }
     } else if (cls == 3) {
-        for (int d = tid; d < g.new_w; d += 256) {
+        for (int d = tid; d < g.new_w; d += PREP_THREADS) {
             int xs, w0, w1, edge;
             linear_coef(d, g.scale_x, g.inv_x, g.w, xs, w0, w1, edge);
             if (edge) { w0 = 2048; w1 = 0; }                        // D = S[sx] * ONE beyond xmax
             xd[d] = make_float4(__int_as_float(w0), __int_as_float(w1), 0.f, __int_as_float(xs));
         }
-        for (int d = tid; d < g.new_h; d += 256) {
+        for (int d = tid; d < g.new_h; d += PREP_THREADS) {
             int s0, b0, b1, edge;
             linear_coef(d, g.scale_y, g.inv_y, g.h, s0, b0, b1, edge);
             const int s1 = min(s0 + 1, g.h - 1);
@@ -1001,7 +1006,7 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
     // class 1 through the warp-specialised CTA kernel: 2-D TMA staging, at most eight strips, full-width boxes inside the pool rows
     const bool use_cta = aligned && T <= CTA_MAX_T && (long long)W * 3 >= cta_pitch_max(T);
     if (BF16 && !use_cta) return BPC_EUNSUPPORTED;       // the bfloat16 output exists on the CTA kernel's path only
-    bpc_crop_prep_kernel<<<R, 256, 0, st>>>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, (aligned ? 1 : 0) | (use_cta ? 2 : 0), geom, xdesc, ydesc,
+    bpc_crop_prep_kernel<<<R, PREP_THREADS, 0, st>>>(images, B, H, W, rois, R, n_rois_dev, roi_first, T, (aligned ? 1 : 0) | (use_cta ? 2 : 0), geom, xdesc, ydesc,
                                             glist, gcount, status, use_cta ? list1 : nullptr);
     BPC_LAUNCH_CHECK();
     const uchar4 f4 = make_uchar4(fill[0], fill[1], fill[2], 0);

@@ -13,6 +13,7 @@ cap() {  # name, kernel regex, skip, command...
 }
 TRAFFIC=config2_chunk16384_T224 cap crop_cta_config2 bpc_crop_cta 8 $B
 cp profiles/crop_traffic.json $O/crop_traffic.json 2>/dev/null
+cap crop_prep_config2 bpc_crop_prep 8 $B
 cap match_config2 bpc_match_kernel 1 $B
 cap match_tri_config2 bpc_match_tri 1 $B
 cap crop_cta_300_900 bpc_crop_cta 3 python tools/crop_sweep.py 300 900 224 16384
