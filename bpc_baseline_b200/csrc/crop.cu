@@ -1015,7 +1015,7 @@ static int launch_crop(const uint8_t* images, int B, int H, int W, const int32_t
                                        outf, outb, st);
         if (rc != BPC_OK) return rc;
     }
-    if (!BF16) {
+    if (!use_cta) {                                       // with the CTA kernel in use every fast-class crop is on ITS list
         typedef void (*WarpFn)(const uint8_t*, int, int, int, const RoiGeom*, const float4*, const float4*, int32_t*, int, int, int,
                                uchar4, int, const float*, float*, uint8_t*, const TmapSet, const int32_t*);
         TmapSet tmaps;
