@@ -295,10 +295,6 @@ bpc_crop_warp_kernel(const uint8_t* __restrict__ images, int B, int H, int W, co
     const unsigned long long img_end = (unsigned long long)(uintptr_t)images + (unsigned long long)B * H * rowstride;
     const float nz = __int_as_float((int)(0x80000000u | (unsigned)fill.w));     // -0.0f: fill.w is 0 at run time
     const u64 nz2 = pack2(nz, nz);
-#if defined(BPC_WHATIF)
-    if (tid == 0) g_whatif_base = outf;
-    __syncthreads();
-#endif
     const long long nitems = (long long)nmine * nslot;
 
     for (;;) {

@@ -287,18 +287,13 @@ __device__ __forceinline__ float4 lds_f4(unsigned addr) {
 }
 
 // output store of the fast paths: the crop buffer is written once and never re-read by this kernel
-#if defined(BPC_WHATIF)
-__device__ float* g_whatif_base;
-#endif
+// (-DBPC_WHATIF=1|2|3: the what-if builds behind DESIGN.md 3.2 -- one plane only / shared-memory stores / no stores)
 template <int K = 0>
 __device__ __forceinline__ void stg_out(float* p, float v) {
 #if defined(BPC_WHATIF) && BPC_WHATIF == 1          // only plane 0 is stored
     if (K == 0) *p = v; else asm volatile("" :: "f"(v));
 #elif defined(BPC_WHATIF) && BPC_WHATIF == 2        // LSU traffic without L2 traffic: the value goes to shared memory
     asm volatile("st.shared.f32 [%0], %1;" :: "r"(((unsigned)(size_t)p) & 0x7cu), "f"(v));
-#elif defined(BPC_WHATIF) && BPC_WHATIF == 4        // stores fold into a 128 KB window per CTA (57 MB in all: stays in L2)
-    float* q = (float*)((size_t)g_whatif_base + ((size_t)blockIdx.x << 17) + (((size_t)p) & 0x1fffc));
-    *q = v;
 #elif defined(BPC_WHATIF) && BPC_WHATIF == 3        // no store, LUT value still loaded
     asm volatile("" :: "f"(v));
 #elif defined(BPC_STG_CS)
