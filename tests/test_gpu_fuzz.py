@@ -71,7 +71,7 @@ def _image(width):
 
 
 @FUZZ
-@given(st.integers(1, 1400), st.integers(1, 1000), st.sampled_from([224, 256, 96, 33]), st.integers(0, 10 ** 6),
+@given(st.integers(1, 1400), st.integers(1, 1000), st.sampled_from([224, 256, 96, 33, 20]), st.integers(0, 10 ** 6),
        st.sampled_from([1500, 1504]))
 def test_crop_any_box(w, h, T, seed, width):
     """Any box (1 px .. nearly the whole image) at several target sizes: uint8 result identical to cv2's, or the
