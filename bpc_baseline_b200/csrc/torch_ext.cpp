@@ -164,6 +164,36 @@ std::tuple<Tensor, Tensor> roi_crop_meta(const Tensor& images, const Tensor& roi
     return {out, at::empty_symint({rois.sym_size(0)}, rois.options())};
 }
 
+// bfloat16 channels-last variant: logical shape [R,3,T,T], memory [R,T,T,3] (what a bf16 tensor-core pose head reads)
+std::tuple<Tensor, Tensor> roi_crop_bf16(const Tensor& images, const Tensor& rois, int64_t T, at::ArrayRef<int64_t> fill, bool swap_rb,
+                                         const Tensor& lut, const c10::optional<Tensor>& n_rois, int64_t roi_first) {
+    crop_common(images, rois, T, fill, n_rois);
+    chk(lut, at::kFloat, "lut", 2);
+    TORCH_CHECK(lut.size(0) == 3 && lut.size(1) == 256, "lut must be [3,256]");
+    const int64_t R = rois.size(0);
+    const c10::cuda::CUDAGuard guard(images.device());
+    Tensor out = at::empty({R, 3, T, T}, lut.options().dtype(at::kBFloat16), at::MemoryFormat::ChannelsLast);
+    Tensor status = at::empty({R}, rois.options());
+    const uint8_t f[3] = {(uint8_t)fill[0], (uint8_t)fill[1], (uint8_t)fill[2]};
+    const int64_t step = 32768;
+    const size_t wsb = bpc_roi_crop_workspace_bytes((int)std::min(R, step), (int)T);
+    Tensor ws = scratch(images, wsb);
+    for (int64_t lo = 0; lo < R; lo += step) {
+        const int64_t r = std::min(step, R - lo);
+        rc_check(bpc_roi_crop_bf16(images.data_ptr<uint8_t>(), (int)images.size(0), (int)images.size(1), (int)images.size(2),
+                                   rois.data_ptr<int32_t>() + lo * 5, (int)r, n_rois.has_value() ? n_rois->data_ptr<int32_t>() : nullptr,
+                                   (int)(roi_first + lo), (int)T, f, swap_rb ? 1 : 0, lut.data_ptr<float>(),
+                                   static_cast<char*>(out.data_ptr()) + lo * 3 * T * T * 2, status.data_ptr<int32_t>() + lo, ws.data_ptr(), wsb,
+                                   cur_stream(images)), "bpc_roi_crop_bf16");
+    }
+    return {out, status};
+}
+
+std::tuple<Tensor, Tensor> roi_crop_bf16_meta(const Tensor& images, const Tensor& rois, int64_t T, at::ArrayRef<int64_t>, bool, const Tensor& lut,
+                                              const c10::optional<Tensor>&, int64_t) {
+    return {at::empty_symint({rois.sym_size(0), 3, T, T}, lut.options().dtype(at::kBFloat16)), at::empty_symint({rois.sym_size(0)}, rois.options())};
+}
+
 std::tuple<Tensor, Tensor> roi_crop_u8(const Tensor& images, const Tensor& rois, int64_t T, at::ArrayRef<int64_t> fill,
                                        const c10::optional<Tensor>& n_rois, int64_t roi_first) {
     crop_common(images, rois, T, fill, n_rois);
@@ -227,6 +257,7 @@ TORCH_LIBRARY(bpc_b200, m) {
     m.def("roi_crop(Tensor images, Tensor rois, int T, int[] fill, bool swap_rb, Tensor lut, Tensor? n_rois=None, int roi_first=0, "
           "Tensor(a!)? out=None) -> (Tensor(a!), Tensor)");
     m.def("roi_crop_u8(Tensor images, Tensor rois, int T, int[] fill, Tensor? n_rois=None, int roi_first=0) -> (Tensor, Tensor)");
+    m.def("roi_crop_bf16(Tensor images, Tensor rois, int T, int[] fill, bool swap_rb, Tensor lut, Tensor? n_rois=None, int roi_first=0) -> (Tensor, Tensor)");
     m.def("pack_records(Tensor idx, Tensor n, Tensor cost, Tensor X, Tensor reproj, Tensor scene_offset, int offset_div=3) -> Tensor");
     m.def("fundamental(Tensor Ks, Tensor RTs) -> Tensor");
     m.def("abi_version() -> int", &abi_version);
@@ -238,6 +269,7 @@ TORCH_LIBRARY_IMPL(bpc_b200, CUDA, m) {
     m.impl("build_rois", &build_rois);
     m.impl("roi_crop", &roi_crop);
     m.impl("roi_crop_u8", &roi_crop_u8);
+    m.impl("roi_crop_bf16", &roi_crop_bf16);
     m.impl("pack_records", &pack_records);
     m.impl("fundamental", &fundamental);
 }
@@ -248,4 +280,5 @@ TORCH_LIBRARY_IMPL(bpc_b200, Meta, m) {
     m.impl("build_rois", &build_rois_meta);
     m.impl("roi_crop", &roi_crop_meta);
     m.impl("roi_crop_u8", &roi_crop_u8_meta);
+    m.impl("roi_crop_bf16", &roi_crop_bf16_meta);
 }

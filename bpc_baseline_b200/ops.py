@@ -76,6 +76,13 @@ def roi_crop_u8(images, rois, T: int = 256, fill=(255, 255, 255), n_rois=None, r
     return load().roi_crop_u8(images, rois, int(T), [int(v) for v in fill], n_rois, int(roi_first))
 
 
+def roi_crop_bf16(images, rois, T: int = 256, fill=(255, 255, 255), swap_rb: bool = True, lut=None, n_rois=None, roi_first: int = 0):
+    """(bfloat16 [R,3,T,T] in channels_last memory format, status): roi_crop's values rounded to bfloat16 (bpc_roi_crop_bf16)."""
+    if lut is None:
+        lut = normalise_lut(images.device)
+    return load().roi_crop_bf16(images, rois, int(T), [int(v) for v in fill], bool(swap_rb), lut, n_rois, int(roi_first))
+
+
 def pack_records(idx, n, cost, X, reproj, scene_offset, offset_div: int = 3):
     return load().pack_records(idx, n, cost, X, reproj, scene_offset, int(offset_div))
 

@@ -205,7 +205,7 @@ def test_torch_extension_loads_and_registers_its_operators():
     build.build_torch_ext()
     o = ops.load()
     assert int(o.abi_version()) == 2
-    for name in ('match_triangulate', 'box_centers', 'build_rois', 'normalise_lut', 'roi_crop', 'roi_crop_u8', 'pack_records', 'fundamental'):
+    for name in ('match_triangulate', 'box_centers', 'build_rois', 'normalise_lut', 'roi_crop', 'roi_crop_u8', 'roi_crop_bf16', 'pack_records', 'fundamental'):
         assert hasattr(o, name), name
     meta = lambda shape, dt: torch.empty(shape, dtype=dt, device='meta')
     r = o.match_triangulate(meta((4, 3, 3, 3), torch.float32), meta((4, 3, 4, 4), torch.float64), meta((4, 3, 9, 2), torch.float64),

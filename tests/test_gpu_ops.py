@@ -36,6 +36,9 @@ def test_ops_equal_the_ctypes_path_bit_for_bit():
     assert torch.equal(_bits(crops), _bits(batched.roi_crop(images, rois_b[:total].contiguous(), T=96))) and int(status.sum()) == 0
     u8, _ = ops.roi_crop_u8(images, rois[:total].contiguous(), 96)
     assert torch.equal(u8, batched.roi_crop_u8(images, rois_b[:total].contiguous(), T=96))
+    b16, st16 = ops.roi_crop_bf16(images, rois[:total].contiguous(), 96)
+    assert b16.is_contiguous(memory_format=torch.channels_last) and int(st16.sum()) == 0
+    assert torch.equal(b16.view(torch.int16), batched.roi_crop_bf16(images, rois_b[:total].contiguous(), T=96).view(torch.int16))
     buf = ops.pack_records(idx, n, cost, X, reproj, offs)
     used = 16 + ((24 * 4 + 15) & ~15) + int(n.clamp(min=0).sum()) * 64          # header | counts | valid records
     assert torch.equal(buf[:used], batched.pack_records(a, offs_b, 3)[:used])
