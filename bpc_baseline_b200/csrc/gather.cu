@@ -38,12 +38,21 @@ struct TileRef {
     int bytes;              // valid bytes in the tile (<= TILE_BYTES)
 };
 
-__device__ __forceinline__ TileRef tile_ref(const GatherSources& g, int n_src, long long item, int tiles, int P, float* out) {
-    const int crop = (int)(item / tiles);
+// `per_src` > 0: every source holds per_src crops and the crops are WALKED round-robin over the sources (crop k of source 0, of
+// source 1, ...), so that tiles of the local source (bound by this GPU's HBM writes) and of the remote ones (bound by the NVLink
+// ingest) are in flight together instead of one phase after the other; the output position of a crop does not change.
+__device__ __forceinline__ TileRef tile_ref(const GatherSources& g, int n_src, int per_src, long long item, int tiles, int P, float* out) {
+    int crop = (int)(item / tiles);
     const int tile = (int)(item - (long long)crop * tiles);
     int s = 0;
+    if (per_src > 0) {
+        const int k = crop / n_src;
+        s = crop - k * n_src;
+        crop = g.first[s] + k;
+    } else {
 #pragma unroll 1
-    while (s + 1 < n_src && crop >= g.first[s + 1]) ++s;
+        while (s + 1 < n_src && crop >= g.first[s + 1]) ++s;
+    }
     TileRef r;
     r.src = g.ptr[s] + ((size_t)(crop - g.first[s]) * P + (size_t)tile * TILE_PIX) * 3;
     r.dst = out + (size_t)crop * 3 * P + (size_t)tile * TILE_PIX;
@@ -59,7 +68,7 @@ __device__ __forceinline__ TileRef tile_ref(const GatherSources& g, int n_src, l
 // the current tile is converted, so a warp always has 1.5 KB in flight (what hides NVLink latency).
 template <bool SWAP>
 __global__ void __launch_bounds__(GATHER_WARPS * 32)
-bpc_crops_normalise_kernel(GatherSources g, int n_src, int T, const float* __restrict__ lut_g, float* __restrict__ out) {
+bpc_crops_normalise_kernel(GatherSources g, int n_src, int per_src, int T, const float* __restrict__ lut_g, float* __restrict__ out) {
     __shared__ float lut[768];
     __shared__ __align__(16) uint8_t stage[GATHER_WARPS][TILE_BYTES];
     for (int e = threadIdx.x; e < 768; e += GATHER_WARPS * 32) lut[e] = lut_g[e];
@@ -73,7 +82,7 @@ bpc_crops_normalise_kernel(GatherSources g, int n_src, int T, const float* __res
     if (item >= nitems) return;
     uint8_t* mine = stage[warp];
 
-    TileRef cur = tile_ref(g, n_src, item, tiles, P, out);
+    TileRef cur = tile_ref(g, n_src, per_src, item, tiles, P, out);
     uint4 v[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -88,7 +97,7 @@ bpc_crops_normalise_kernel(GatherSources g, int n_src, int T, const float* __res
         const bool more = next < nitems;
         TileRef nxt = cur;
         if (more) {
-            nxt = tile_ref(g, n_src, next, tiles, P, out);
+            nxt = tile_ref(g, n_src, per_src, next, tiles, P, out);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const int off = (k * 32 + lane) * 16;
@@ -174,7 +183,10 @@ extern "C" int bpc_crops_normalise(const uint8_t* const* srcs, const int32_t* co
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, GATHER_WARPS * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
         const long long slots = (long long)sms * per_sm;
         const int grid = (int)(want < slots ? want : slots);
-        fn<<<grid, GATHER_WARPS * 32, 0, st>>>(g, n_src, T, lut, out);
+        int per_src = n_src > 1 ? counts[0] : 0;                 // equal counts: walk the sources round-robin
+        for (int s2 = 1; s2 < n_src; ++s2)
+            if (counts[s2] != counts[0]) per_src = 0;
+        fn<<<grid, GATHER_WARPS * 32, 0, st>>>(g, n_src, per_src, T, lut, out);
     } else {
         bpc_crops_normalise_any_kernel<<<sms * 8, 256, 0, st>>>(g, n_src, T, swap_rb, lut, out);
     }
